@@ -1,0 +1,72 @@
+// common.cuh -- shared definitions for the helmnet sm_100a kernels.
+//
+// The same kernel sources compile in two modes:
+//   * nvcc, -gencode arch=compute_100a,code=sm_100a  -> libhelmnet_sm100.so (the product)
+//   * g++ -DHN_EMU (tests/emu/)                       -> a fiber-based functional emulator used ONLY by
+//     the CPU test-suite to exercise kernel index logic without a GPU.  It is never loaded by the
+//     helmnet_b200 package.
+#pragma once
+
+#ifdef HN_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+#include <stdint.h>
+
+#ifdef HN_EMU
+#define HN_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    hn_emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
+#else
+#define HN_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+// dynamic shared memory of the running CTA
+#ifdef HN_EMU
+#define HN_DYN_SMEM(type, name) \
+    type* name = reinterpret_cast<type*>((reinterpret_cast<uintptr_t>(hn_emu::g.dyn_smem) + 1023) & ~uintptr_t(1023))
+#else
+#define HN_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#endif
+
+namespace hn {
+
+constexpr int kDepth = 4;         // encoder levels with hidden state (ckpt: depth=4, state_depth=4)
+constexpr int kFeat = 8;          // feature channels
+
+// ---- packed fp32 FMA (Blackwell FFMA2: two fp32 FMAs per issue slot) --------------------------------
+// d.{x,y} += a * b.{x,y}.  ptxas folds the {a,a} pack into FFMA2's scalar-broadcast operand form.
+__device__ __forceinline__ void ffma2(float2& d, float a, float2 b) {
+#if defined(HN_EMU) || defined(HN_NO_FFMA2)
+    d.x = fmaf(a, b.x, d.x);
+    d.y = fmaf(a, b.y, d.y);
+#else
+    asm("{ .reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %2};\n\t"
+        "mov.b64 rb, {%3, %4};\n\t"
+        "mov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rc; }"
+        : "+f"(d.x), "+f"(d.y)
+        : "f"(a), "f"(b.x), "f"(b.y));
+#endif
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.y * b.x + a.x * b.y);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace hn

@@ -1,0 +1,933 @@
+// helmnet_sm100.cu -- C ABI (include/helmnet_sm100.h) and host-side orchestration of the helmnet
+// inference inner loop on one B200.
+//
+// One hn_ctx owns, resident in HBM for the whole solve: wavefield, residual, k_sq, source, hidden states
+// (ping-pong), every UNet activation, operator tables, packed weights.  One solver iteration
+// (IterativeSolver.single_step, helmnet/hybridnet.py:558-584) is a fixed sequence of kernels that is
+// captured once per (batch, state parity) into a CUDA graph and replayed; nothing is allocated, copied
+// to the host or synchronised inside hn_run.
+#include "../../include/helmnet_sm100.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_simt.cuh"
+#include "layout.cuh"
+#include "spectral.cuh"
+
+using namespace hn;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define HN_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(HN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                                         std::to_string(__LINE__) + ")");                               \
+    } while (0)
+#define HN_TRY(expr)             \
+    do {                         \
+        int rc_ = (expr);        \
+        if (rc_ != HN_OK) return rc_; \
+    } while (0)
+
+struct ConvW {      // offsets (in floats) into the packed device blob
+    size_t w = 0, b = 0, slope = 0;
+};
+struct Weights {
+    ConvW inc[2], sig[kDepth][2], sta[kDepth][2], down[kDepth], bot[2], up[kDepth], dec[kDepth][2], outc;
+};
+
+struct hn_ctx {
+    int device = 0, n = 0, max_batch = 0, pml = 0;
+    double sigma_max = 0, k0 = 1, omega = 1;
+    int r[kDepth + 1] = {0};
+    int state_len = 0;
+    int engine = 0;
+    // resident fields
+    float *wf = nullptr, *res = nullptr, *ksq = nullptr, *src = nullptr, *rx = nullptr;
+    float* state[kDepth][2] = {{nullptr}};
+    int cur = 0;
+    int src_batch = 0, batch = 0;
+    bool weights_set = false, problem_set = false;
+    // UNet activations (NHWC8 unless noted)
+    float* x[kDepth + 1] = {nullptr};
+    float* mid[kDepth + 1] = {nullptr};
+    float* mid2[kDepth] = {nullptr};   // float2
+    float* skip[kDepth] = {nullptr};
+    float* upo[kDepth] = {nullptr};
+    float* dec[kDepth] = {nullptr};
+    float* bot = nullptr;
+    float* in6 = nullptr;   // NHWC8 staging for hn_unet
+    float* dwf = nullptr;   // float2 raw network output for hn_unet
+    float* tmp2 = nullptr;  // float2 scratch [B][n][n] (hn_residual / hn_laplacian inputs)
+    float* tmp2b = nullptr;
+    // tables
+    SpecTables spec;
+    float* sigma1d = nullptr;
+    int rows_L = 1, cols_CW = 1;
+    // weights
+    float* wdev = nullptr;
+    Weights W;
+    // residual norms
+    double* ssq = nullptr;
+    size_t ssq_cap = 0;
+    double* ssq1 = nullptr;   // [max_batch] for hn_residual
+    int* iter_dev = nullptr;  // [0] = running slot, [1] = constant 0
+    // launch accounting + graphs
+    int64_t launches = 0;
+    int kernels_per_iter = 0;
+    bool use_graph = true;
+#ifndef HN_EMU
+    std::map<long long, cudaGraphExec_t> graphs;
+#endif
+    std::vector<void*> allocs;
+};
+
+static int dalloc(hn_ctx* c, void** p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) return fail(HN_ERR_NOMEM, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    c->allocs.push_back(*p);
+    return HN_OK;
+}
+template <typename T>
+static int dalloc_t(hn_ctx* c, T** p, size_t count) {
+    return dalloc(c, reinterpret_cast<void**>(p), count * sizeof(T));
+}
+
+static inline int grid1d(size_t total) {
+    size_t g = (total + LAY_THREADS - 1) / LAY_THREADS;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Operator tables (helmnet/spectral.py:122-146, 267-363), computed in double precision on the host.
+// ------------------------------------------------------------------------------------------------
+static void factorize(int n, int* radix, int* nst) {
+    int k = 0;
+    while (n % 4 == 0) { radix[k++] = 4; n /= 4; }
+    while (n % 2 == 0) { radix[k++] = 2; n /= 2; }
+    for (int p = 3; n > 1; p += 2)
+        while (n % p == 0) { radix[k++] = p; n /= p; }
+    *nst = k;
+}
+
+static int build_tables(hn_ctx* c) {
+    const int n = c->n, pml = c->pml;
+    std::vector<float> tw(2 * n), mk(n), msq(n), a(2 * n, 0.f), b(2 * n), sig(n, 0.f);
+    const double PI = 3.14159265358979323846;
+    for (int k = 0; k < n; k++) {
+        const double ang = -2.0 * PI * (double)k / (double)n;
+        tw[2 * k] = (float)cos(ang);
+        tw[2 * k + 1] = (float)sin(ang);
+    }
+    // spectral.py:126-127: k = 2 pi linspace(-0.5, 0.5, n, endpoint=False), rotated by n/2, cast to float32 (:141)
+    for (int i = 0; i < n; i++) {
+        const int j = (i + n / 2) % n;                       // position in the un-rotated linspace
+        const double kd = 2.0 * PI * (-0.5 + (double)j * (1.0 / (double)n));
+        const float k32 = (float)kd;
+        const float ksq32 = k32 * k32;                       // spectral.py:281 float32 pow(2)
+        mk[i] = (float)((double)k32 / (double)n);
+        msq[i] = (float)(-(double)ksq32 / (double)n);
+    }
+    // spectral.py:306-338
+    std::vector<double> sigma(n, 0.0), sprime(n, 0.0);
+    for (int i = 0; i < pml; i++) {
+        const double so = c->sigma_max * pow(fabs(1.0 - (double)i / (double)pml), 2.0);
+        const double sp = -2.0 * c->sigma_max * (1.0 - (double)i / (double)pml) / (double)pml;
+        sigma[i] = so;
+        sigma[n - 1 - i] = so;
+        sprime[i] = sp;
+        sprime[n - 1 - i] = -sp;
+    }
+    for (int i = 0; i < n; i++) {
+        // inv_gamma = 1 / (1 + (i/k0) sigma);  gamma' = (i/k0) sigma'
+        const double s = sigma[i] / c->k0, d = 1.0 + s * s;
+        const double gr = 1.0 / d, gi = -s / d;              // inv_gamma
+        const double g2r = gr * gr - gi * gi, g2i = 2.0 * gr * gi;          // inv_gamma^2  = b
+        const double g3r = g2r * gr - g2i * gi, g3i = g2r * gi + g2i * gr;  // inv_gamma^3
+        const double gpi = sprime[i] / c->k0;                // gamma' = i * gpi
+        // a = -gamma' * inv_gamma^3 = -(i gpi)(g3r + i g3i) = gpi*g3i - i gpi*g3r
+        a[2 * i] = (float)(gpi * g3i);
+        a[2 * i + 1] = (float)(-gpi * g3r);
+        b[2 * i] = (float)g2r;
+        b[2 * i + 1] = (float)g2i;
+        sig[i] = (float)sigma[i];
+    }
+    float *d_tw, *d_mk, *d_msq, *d_a, *d_b;
+    HN_TRY(dalloc_t(c, &d_tw, 2 * n));
+    HN_TRY(dalloc_t(c, &d_mk, n));
+    HN_TRY(dalloc_t(c, &d_msq, n));
+    HN_TRY(dalloc_t(c, &d_a, 2 * n));
+    HN_TRY(dalloc_t(c, &d_b, 2 * n));
+    HN_TRY(dalloc_t(c, &c->sigma1d, n));
+    HN_CUDA(cudaMemcpy(d_tw, tw.data(), 2 * n * 4, cudaMemcpyHostToDevice));
+    HN_CUDA(cudaMemcpy(d_mk, mk.data(), n * 4, cudaMemcpyHostToDevice));
+    HN_CUDA(cudaMemcpy(d_msq, msq.data(), n * 4, cudaMemcpyHostToDevice));
+    HN_CUDA(cudaMemcpy(d_a, a.data(), 2 * n * 4, cudaMemcpyHostToDevice));
+    HN_CUDA(cudaMemcpy(d_b, b.data(), 2 * n * 4, cudaMemcpyHostToDevice));
+    HN_CUDA(cudaMemcpy(c->sigma1d, sig.data(), n * 4, cudaMemcpyHostToDevice));
+    c->spec.tw = reinterpret_cast<const float2*>(d_tw);
+    c->spec.mk = d_mk;
+    c->spec.msq = d_msq;
+    c->spec.a = reinterpret_cast<const float2*>(d_a);
+    c->spec.b = reinterpret_cast<const float2*>(d_b);
+    c->spec.n = n;
+    c->spec.pml = pml;
+    factorize(n, c->spec.radix, &c->spec.nstages);
+    // lines per CTA: ~48 KB of line buffers for the row pass; the column pass needs >= 32 B segments
+    int L = 2048 / n;
+    if (L < 1) L = 1;
+    if (L > 16) L = 16;
+    c->rows_L = L;
+    int CW = 16;
+    while (CW > 1 && spectral_smem_bytes(n, CW, pml) > (n <= 256 ? 110 * 1024 : 200 * 1024)) CW >>= 1;
+    c->cols_CW = CW;
+    if (spectral_smem_bytes(n, CW, pml) > 227 * 1024) return fail(HN_ERR_ARG, "domain size too large for one line per CTA");
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights: state_dict order of HybridNet (helmnet/architectures.py:317-388) -> packed device layouts
+// ------------------------------------------------------------------------------------------------
+struct Packer {
+    std::vector<float> blob;
+    size_t reserve(size_t nfl) {
+        size_t off = (blob.size() + 3) & ~(size_t)3;
+        blob.resize(off + nfl, 0.f);
+        return off;
+    }
+};
+// W[co][ci][3][3] -> P[pl][tap][ci4][co]
+static size_t pack_conv3(Packer& pk, const float* w, int cout, int cin) {
+    const int npl = (cin + 3) / 4;
+    size_t off = pk.reserve((size_t)npl * 9 * 4 * cout);
+    for (int pl = 0; pl < npl; pl++)
+        for (int tap = 0; tap < 9; tap++)
+            for (int c4 = 0; c4 < 4; c4++)
+                for (int co = 0; co < cout; co++) {
+                    const int ci = pl * 4 + c4;
+                    pk.blob[off + ((pl * 9 + tap) * 4 + c4) * cout + co] = ci < cin ? w[(co * cin + ci) * 9 + tap] : 0.f;
+                }
+    return off;
+}
+// W[co][ci][8][8] -> P[pl][ky][kx][ci4][co]
+static size_t pack_down(Packer& pk, const float* w) {
+    size_t off = pk.reserve(2 * 64 * 4 * 8);
+    for (int pl = 0; pl < 2; pl++)
+        for (int k = 0; k < 64; k++)
+            for (int c4 = 0; c4 < 4; c4++)
+                for (int co = 0; co < 8; co++) pk.blob[off + ((pl * 64 + k) * 4 + c4) * 8 + co] = w[(co * 8 + pl * 4 + c4) * 64 + k];
+    return off;
+}
+// ConvTranspose weight W[ci][co][8][8] -> P[cls][pl][ty][tx][ci4][co],  ky = 7 - 2ty - py, kx = 7 - 2tx - px
+static size_t pack_up(Packer& pk, const float* w) {
+    size_t off = pk.reserve(4 * 2 * 16 * 4 * 8);
+    for (int cls = 0; cls < 4; cls++) {
+        const int py = cls >> 1, px = cls & 1;
+        for (int pl = 0; pl < 2; pl++)
+            for (int ty = 0; ty < 4; ty++)
+                for (int tx = 0; tx < 4; tx++)
+                    for (int c4 = 0; c4 < 4; c4++)
+                        for (int co = 0; co < 8; co++) {
+                            const int ky = 7 - 2 * ty - py, kx = 7 - 2 * tx - px, ci = pl * 4 + c4;
+                            pk.blob[off + ((((cls * 2 + pl) * 4 + ty) * 4 + tx) * 4 + c4) * 8 + co] = w[((ci * 8 + co) * 8 + ky) * 8 + kx];
+                        }
+    }
+    return off;
+}
+static size_t pack_vec(Packer& pk, const float* v, int nfl) {
+    size_t off = pk.reserve(nfl);
+    for (int i = 0; i < nfl; i++) pk.blob[off + i] = v[i];
+    return off;
+}
+
+struct Cursor {
+    const float* p;
+    size_t left;
+    bool ok = true;
+    const float* take(size_t nfl) {
+        if (nfl > left) { ok = false; return p; }
+        const float* q = p;
+        p += nfl;
+        left -= nfl;
+        return q;
+    }
+};
+static void pack_double_conv(Packer& pk, Cursor& cur, ConvW out[2], int cin, int cmid, int cout) {
+    const float* w0 = cur.take((size_t)cmid * cin * 9);
+    const float* b0 = cur.take(cmid);
+    const float* sl = cur.take(1);
+    const float* w1 = cur.take((size_t)cout * cmid * 9);
+    const float* b1 = cur.take(cout);
+    if (!cur.ok) return;
+    out[0].w = pack_conv3(pk, w0, cmid, cin);
+    out[0].b = pack_vec(pk, b0, cmid);
+    out[0].slope = pack_vec(pk, sl, 1);
+    out[1].w = pack_conv3(pk, w1, cout, cmid);
+    out[1].b = pack_vec(pk, b1, cout);
+    out[1].slope = out[0].slope;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel launch helpers
+// ------------------------------------------------------------------------------------------------
+template <int SRC, int COUT, bool PRELU, int EPI>
+static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
+    const size_t smem = conv3_smem_bytes(SRC, COUT);
+#ifndef HN_EMU
+    static bool attr_done[16] = {false};
+    if (!attr_done[c->device & 15]) {
+        HN_CUDA(cudaFuncSetAttribute(conv3x3_kernel<SRC, COUT, PRELU, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[c->device & 15] = true;
+    }
+#endif
+    dim3 grid((a.W + C3_TX - 1) / C3_TX, (a.H + C3_TY - 1) / C3_TY, B);
+    HN_LAUNCH((conv3x3_kernel<SRC, COUT, PRELU, EPI>), grid, dim3(C3_THREADS), smem, st, a);
+    c->launches++;
+    return HN_OK;
+}
+
+static Conv3Args conv_args(hn_ctx* c, const ConvW& w, const float* inA, const float* inB, float* out, int r) {
+    Conv3Args a;
+    memset(&a, 0, sizeof(a));
+    a.inA = inA;
+    a.inB = inB;
+    a.sigma = c->sigma1d;
+    a.w = c->wdev + w.w;
+    a.bias = c->wdev + w.b;
+    a.slope = c->wdev + w.slope;
+    a.out = out;
+    a.H = r;
+    a.W = r;
+    return a;
+}
+
+#ifndef HN_EMU
+static int set_smem_attrs(hn_ctx* c) {
+    HN_CUDA(cudaFuncSetAttribute(down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DN_SMEM));
+    HN_CUDA(cudaFuncSetAttribute(up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UP_SMEM));
+    HN_CUDA(cudaFuncSetAttribute(spectral_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)spectral_smem_bytes(c->n, c->rows_L, c->pml)));
+    HN_CUDA(cudaFuncSetAttribute(spectral_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)spectral_smem_bytes(c->n, c->cols_CW, c->pml)));
+    return HN_OK;
+}
+#endif
+
+// HybridNet.forward (architectures.py:439-465).  `from_in6`: read the 6-channel input from c->in6 instead of
+// building it from (wf, 1e3*res, sigmas); `raw_out`: store the network output to c->dwf instead of updating wf.
+static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool raw_out) {
+    const Weights& W = c->W;
+    const int cur = c->cur, nxt = cur ^ 1;
+    // inc
+    {
+        Conv3Args a = conv_args(c, W.inc[0], from_in6 ? c->in6 : c->wf, c->res, c->mid[0], c->r[0]);
+        if (from_in6) HN_TRY((launch_conv3<SRC_A8, 8, true, EPI_STORE>(c, a, B, st)));
+        else HN_TRY((launch_conv3<SRC_INC, 8, true, EPI_STORE>(c, a, B, st)));
+        Conv3Args a2 = conv_args(c, W.inc[1], c->mid[0], nullptr, c->x[0], c->r[0]);
+        HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, a2, B, st)));
+    }
+    // encoder
+    for (int d = 0; d < kDepth; d++) {
+        const int r = c->r[d];
+        Conv3Args s0 = conv_args(c, W.sig[d][0], c->x[d], c->state[d][cur], c->mid[d], r);
+        HN_TRY((launch_conv3<SRC_A8_B2, 8, true, EPI_STORE>(c, s0, B, st)));
+        Conv3Args s1 = conv_args(c, W.sig[d][1], c->mid[d], nullptr, c->skip[d], r);
+        HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, s1, B, st)));
+        Conv3Args t0 = conv_args(c, W.sta[d][0], c->skip[d], c->state[d][cur], c->mid2[d], r);
+        HN_TRY((launch_conv3<SRC_A8_B2, 2, true, EPI_STORE>(c, t0, B, st)));
+        Conv3Args t1 = conv_args(c, W.sta[d][1], c->mid2[d], nullptr, c->state[d][nxt], r);
+        HN_TRY((launch_conv3<SRC_A2, 2, false, EPI_STORE>(c, t1, B, st)));
+        DownArgs dn;
+        dn.in = c->skip[d];
+        dn.w = c->wdev + W.down[d].w;
+        dn.bias = c->wdev + W.down[d].b;
+        dn.out = c->x[d + 1];
+        dn.H = r;
+        dn.W = r;
+        dim3 g((r / 2 + DN_TX - 1) / DN_TX, (r / 2 + DN_TY - 1) / DN_TY, B);
+        HN_LAUNCH(down_kernel, g, dim3(DN_THREADS), DN_SMEM, st, dn);
+        c->launches++;
+    }
+    // bottom
+    {
+        const int r = c->r[kDepth];
+        Conv3Args b0 = conv_args(c, W.bot[0], c->x[kDepth], nullptr, c->mid[kDepth], r);
+        HN_TRY((launch_conv3<SRC_A8, 8, true, EPI_STORE>(c, b0, B, st)));
+        Conv3Args b1 = conv_args(c, W.bot[1], c->mid[kDepth], nullptr, c->bot, r);
+        HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, b1, B, st)));
+    }
+    // decoder
+    for (int d = kDepth - 1; d >= 0; d--) {
+        const int r = c->r[d];
+        UpArgs up;
+        up.in = (d == kDepth - 1) ? c->bot : c->dec[d + 1];
+        up.w = c->wdev + W.up[d].w;
+        up.bias = c->wdev + W.up[d].b;
+        up.out = c->upo[d];
+        up.Hi = r / 2;
+        up.Wi = r / 2;
+        dim3 g((r / 2 + UP_TL - 1) / UP_TL, (r / 2 + UP_TL - 1) / UP_TL, B);
+        HN_LAUNCH(up_kernel, g, dim3(UP_THREADS), UP_SMEM, st, up);
+        c->launches++;
+        Conv3Args d0 = conv_args(c, W.dec[d][0], c->upo[d], c->skip[d], c->mid[d], r);
+        HN_TRY((launch_conv3<SRC_A8_B8, 8, true, EPI_STORE>(c, d0, B, st)));
+        Conv3Args d1 = conv_args(c, W.dec[d][1], c->mid[d], nullptr, c->dec[d], r);
+        if (d > 0) {
+            HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, d1, B, st)));
+        } else {
+            d1.wo = c->wdev + W.outc.w;
+            d1.bo = c->wdev + W.outc.b;
+            d1.wf = c->wf;
+            d1.dwf_out = raw_out ? c->dwf : nullptr;
+            HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_OUTC>(c, d1, B, st)));
+        }
+    }
+    return HN_OK;
+}
+
+// r = L(u) + ksq*u - src  (any of ksq/src/ssq may be null)
+static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, const float* ksq, const float* src,
+                           int src_batch, float* res, double* ssq, const int* slot) {
+    const int n = c->n;
+    const int total_rows = B * n;
+    const int L = c->rows_L, CW = c->cols_CW;
+    HN_LAUNCH(spectral_rows_kernel, dim3((total_rows + L - 1) / L), dim3(SPEC_THREADS), spectral_smem_bytes(n, L, c->pml),
+              st, c->spec, reinterpret_cast<const float2*>(u), reinterpret_cast<float2*>(c->rx), total_rows, L);
+    ColsArgs a;
+    a.u = reinterpret_cast<const float2*>(u);
+    a.rx = reinterpret_cast<const float2*>(c->rx);
+    a.ksq = ksq;
+    a.src = reinterpret_cast<const float2*>(src);
+    a.res = reinterpret_cast<float2*>(res);
+    a.ssq = ssq;
+    a.slot = slot;
+    a.src_batch = src_batch;
+    a.B = B;
+    a.CW = CW;
+    HN_LAUNCH(spectral_cols_kernel, dim3((n + CW - 1) / CW, B), dim3(SPEC_THREADS), spectral_smem_bytes(n, CW, c->pml), st,
+              c->spec, a);
+    c->launches += 2;
+    return HN_OK;
+}
+
+static int launch_iteration(hn_ctx* c, int B, cudaStream_t st) {
+    HN_TRY(launch_unet(c, B, st, false, false));
+    HN_TRY(launch_spectral(c, B, st, c->wf, c->ksq, c->src, c->src_batch, c->res, c->ssq, c->iter_dev));
+    HN_LAUNCH(advance_iter_kernel, dim3(1), dim3(32), 0, st, c->iter_dev);
+    c->launches++;
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* hn_version(void) {
+#ifdef HN_EMU
+    return "helmnet_sm100 0.1.0 EMULATOR (tests only)";
+#else
+    return "helmnet_sm100 0.1.0 sm_100a";
+#endif
+}
+const char* hn_last_error(void) { return g_err.c_str(); }
+
+int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, double sigma_max, double k0, double omega) {
+    if (!out) return fail(HN_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (n <= 0 || n % 16 != 0) return fail(HN_ERR_ARG, "domain size must be a positive multiple of 16");
+    if (max_batch <= 0) return fail(HN_ERR_ARG, "max_batch must be positive");
+    if (pml_size < 0 || 2 * pml_size > n) return fail(HN_ERR_ARG, "PML does not fit the domain");
+    if (k0 == 0.0) return fail(HN_ERR_ARG, "k must be non-zero");
+#ifndef HN_EMU
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(HN_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(HN_ERR_ARG, "bad device ordinal");
+    HN_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HN_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(HN_ERR_CUDA, "libhelmnet_sm100 needs a compute capability 10.x (Blackwell) device");
+#endif
+    hn_ctx* c = new hn_ctx();
+    c->device = device;
+    c->n = n;
+    c->max_batch = max_batch;
+    c->pml = pml_size;
+    c->sigma_max = sigma_max;
+    c->k0 = k0;
+    c->omega = omega;
+    c->state_len = 0;
+    for (int d = 0; d <= kDepth; d++) c->r[d] = n >> d;
+    for (int d = 0; d < kDepth; d++) c->state_len += c->r[d] * c->r[d];
+    const char* ng = getenv("HELMNET_NO_GRAPH");
+    c->use_graph = !(ng && ng[0] == '1');
+#ifdef HN_EMU
+    c->use_graph = false;
+#endif
+    auto cleanup = [&](int rc) {
+        hn_destroy(c);
+        return rc;
+    };
+    int rc = build_tables(c);
+    if (rc != HN_OK) return cleanup(rc);
+    const size_t B = (size_t)max_batch, hw = (size_t)n * n;
+#define A_(ptr, cnt)                                      \
+    do {                                                  \
+        rc = dalloc_t(c, &(ptr), (cnt));                  \
+        if (rc != HN_OK) return cleanup(rc);              \
+    } while (0)
+    A_(c->wf, B * hw * 2);
+    A_(c->res, B * hw * 2);
+    A_(c->ksq, B * hw);
+    A_(c->src, B * hw * 2);
+    A_(c->rx, B * hw * 2);
+    A_(c->tmp2, B * hw * 2);
+    A_(c->tmp2b, B * hw * 2);
+    A_(c->dwf, B * hw * 2);
+    A_(c->in6, B * hw * 8);
+    for (int d = 0; d <= kDepth; d++) {
+        const size_t p = (size_t)c->r[d] * c->r[d];
+        A_(c->x[d], B * p * 8);
+        A_(c->mid[d], B * p * 8);
+        if (d < kDepth) {
+            A_(c->state[d][0], B * p * 2);
+            A_(c->state[d][1], B * p * 2);
+            A_(c->mid2[d], B * p * 2);
+            A_(c->skip[d], B * p * 8);
+            A_(c->upo[d], B * p * 8);
+            A_(c->dec[d], B * p * 8);
+        }
+    }
+    A_(c->bot, B * (size_t)c->r[kDepth] * c->r[kDepth] * 8);
+    A_(c->ssq1, B);
+    A_(c->iter_dev, 4);
+    A_(c->wdev, 65536);
+#undef A_
+    if (cudaMemset(c->iter_dev, 0, 16) != cudaSuccess) return cleanup(fail(HN_ERR_CUDA, "cudaMemset failed"));
+    for (int d = 0; d < kDepth; d++)
+        for (int k = 0; k < 2; k++)
+            if (cudaMemset(c->state[d][k], 0, B * (size_t)c->r[d] * c->r[d] * 8) != cudaSuccess)
+                return cleanup(fail(HN_ERR_CUDA, "cudaMemset failed"));
+#ifndef HN_EMU
+    rc = set_smem_attrs(c);
+    if (rc != HN_OK) return cleanup(rc);
+#endif
+    *out = c;
+    return HN_OK;
+}
+
+int hn_destroy(hn_ctx* c) {
+    if (!c) return HN_OK;
+#ifndef HN_EMU
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+#endif
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->ssq) cudaFree(c->ssq);
+    delete c;
+    return HN_OK;
+}
+
+int hn_load_weights(hn_ctx* c, const float* host_blob, size_t n_floats) {
+    if (!c || !host_blob) return fail(HN_ERR_ARG, "NULL argument");
+    if (n_floats != HN_NUM_WEIGHTS) return fail(HN_ERR_ARG, "expected 48160 floats (HybridNet features=8 depth=4 state=2)");
+    Packer pk;
+    Cursor cur{host_blob, n_floats};
+    Weights& W = c->W;
+    pack_double_conv(pk, cur, W.inc, 6, 8, 8);
+    for (int d = 0; d < kDepth; d++) {   // module order inside EncoderBlock: conv_signal, down, conv_state
+        pack_double_conv(pk, cur, W.sig[d], 10, 8, 8);
+        const float* dw = cur.take(8 * 8 * 64);
+        const float* db = cur.take(8);
+        if (cur.ok) {
+            W.down[d].w = pack_down(pk, dw);
+            W.down[d].b = pack_vec(pk, db, 8);
+        }
+        pack_double_conv(pk, cur, W.sta[d], 10, 2, 2);
+    }
+    for (int d = 0; d < kDepth; d++) pack_double_conv(pk, cur, W.dec[d], 16, 8, 8);
+    pack_double_conv(pk, cur, W.bot, 8, 8, 8);   // decode[depth]
+    for (int d = 0; d < kDepth; d++) {
+        const float* uw = cur.take(8 * 8 * 64);
+        const float* ub = cur.take(8);
+        if (cur.ok) {
+            W.up[d].w = pack_up(pk, uw);
+            W.up[d].b = pack_vec(pk, ub, 8);
+        }
+    }
+    {
+        const float* ow = cur.take(16);
+        const float* ob = cur.take(2);
+        if (cur.ok) {
+            W.outc.w = pack_vec(pk, ow, 16);
+            W.outc.b = pack_vec(pk, ob, 2);
+        }
+    }
+    if (!cur.ok || cur.left != 0) return fail(HN_ERR_ARG, "weight blob does not match the HybridNet state_dict layout");
+    if (pk.blob.size() > 65536) return fail(HN_ERR_STATE, "packed weights exceed the reserved buffer");
+#ifndef HN_EMU
+    HN_CUDA(cudaSetDevice(c->device));
+    HN_CUDA(cudaDeviceSynchronize());
+#endif
+    HN_CUDA(cudaMemcpy(c->wdev, pk.blob.data(), pk.blob.size() * 4, cudaMemcpyHostToDevice));
+    c->weights_set = true;
+    return HN_OK;
+}
+
+int hn_set_source(hn_ctx* c, const float* d_src, int src_batch, const int64_t strides[4], void* stream) {
+    if (!c || !d_src || !strides) return fail(HN_ERR_ARG, "NULL argument");
+    if (src_batch < 1 || src_batch > c->max_batch) return fail(HN_ERR_ARG, "source batch out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t total = (size_t)src_batch * c->n * c->n;
+    HN_LAUNCH(src_strided_to_c2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_src,
+              reinterpret_cast<float2*>(c->src), c->n, total, (long long)strides[0], (long long)strides[1],
+              (long long)strides[2], (long long)strides[3]);
+    c->launches++;
+    HN_CUDA(cudaGetLastError());
+    c->src_batch = src_batch;
+    return HN_OK;
+}
+
+static int check_ready(hn_ctx* c, int batch) {
+    if (!c) return fail(HN_ERR_ARG, "ctx is NULL");
+    if (batch < 1 || batch > c->max_batch) return fail(HN_ERR_ARG, "batch out of range for this context");
+    if (!c->weights_set) return fail(HN_ERR_STATE, "hn_load_weights has not been called");
+    if (c->src_batch == 0) return fail(HN_ERR_STATE, "hn_set_source has not been called");
+    if (c->src_batch != 1 && c->src_batch != batch) return fail(HN_ERR_ARG, "source batch must be 1 or equal to the batch");
+    return HN_OK;
+}
+
+int hn_reset(hn_ctx* c, const float* d_sos, int batch, void* stream) {
+    HN_TRY(check_ready(c, batch));
+    if (!d_sos) return fail(HN_ERR_ARG, "d_sos is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int hw = c->n * c->n;
+    const size_t total = (size_t)batch * hw;
+    HN_LAUNCH(reset_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_sos, c->ksq, reinterpret_cast<float2*>(c->wf),
+              reinterpret_cast<float2*>(c->res), reinterpret_cast<const float2*>(c->src), c->src_batch, (float)c->omega, hw,
+              total);
+    c->launches++;
+    for (int d = 0; d < kDepth; d++)
+        HN_CUDA(cudaMemsetAsync(c->state[d][c->cur], 0, (size_t)batch * c->r[d] * c->r[d] * 8, st));
+    HN_CUDA(cudaGetLastError());
+    c->batch = batch;
+    c->problem_set = true;
+    return HN_OK;
+}
+
+int hn_set_state(hn_ctx* c, const float* d_wf, const float* d_res, const float* d_ksq, const float* d_hflat, int batch,
+                 void* stream) {
+    HN_TRY(check_ready(c, batch));
+    if (!(d_wf && d_res && d_ksq) && (d_wf || d_res || d_ksq) && !(c->problem_set && c->batch == batch))
+        return fail(HN_ERR_STATE, "partial field update needs an existing solve state of the same batch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int hw = c->n * c->n;
+    const size_t total = (size_t)batch * hw;
+    if (d_wf) {
+        HN_LAUNCH(nchw2_to_c2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_wf, reinterpret_cast<float2*>(c->wf), hw, total);
+        c->launches++;
+    }
+    if (d_res) {
+        HN_LAUNCH(nchw2_to_c2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_res, reinterpret_cast<float2*>(c->res), hw, total);
+        c->launches++;
+    }
+    if (d_ksq) HN_CUDA(cudaMemcpyAsync(c->ksq, d_ksq, total * 4, cudaMemcpyDeviceToDevice, st));
+    if (d_hflat) {
+        size_t off = 0;
+        for (int d = 0; d < kDepth; d++) {
+            const int p = c->r[d] * c->r[d];
+            const size_t tot = (size_t)batch * p;
+            HN_LAUNCH(nchw2_strided_to_c2_kernel, dim3(grid1d(tot)), dim3(LAY_THREADS), 0, st, d_hflat + off,
+                      reinterpret_cast<float2*>(c->state[d][c->cur]), p, tot, (size_t)2 * c->state_len, (size_t)c->state_len);
+            c->launches++;
+            off += p;
+        }
+    }
+    HN_CUDA(cudaGetLastError());
+    if (d_wf && d_res && d_ksq) {
+        c->batch = batch;
+        c->problem_set = true;
+    }
+    return HN_OK;
+}
+
+static int copy_states_out(hn_ctx* c, float* d_hflat, int batch, cudaStream_t st) {
+    size_t off = 0;
+    for (int d = 0; d < kDepth; d++) {
+        const int p = c->r[d] * c->r[d];
+        const size_t tot = (size_t)batch * p;
+        HN_LAUNCH(c2_to_nchw2_kernel, dim3(grid1d(tot)), dim3(LAY_THREADS), 0, st,
+                  reinterpret_cast<const float2*>(c->state[d][c->cur]), d_hflat + off, p, tot, (size_t)2 * c->state_len,
+                  (size_t)c->state_len);
+        c->launches++;
+        off += p;
+    }
+    return HN_OK;
+}
+
+int hn_get(hn_ctx* c, float* d_wf, float* d_res, float* d_hflat, void* stream) {
+    if (!c) return fail(HN_ERR_ARG, "ctx is NULL");
+    if (!c->problem_set) return fail(HN_ERR_STATE, "no solve state: call hn_reset or hn_set_state first");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int hw = c->n * c->n;
+    const size_t total = (size_t)c->batch * hw;
+    if (d_wf) {
+        HN_LAUNCH(c2_to_nchw2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, reinterpret_cast<const float2*>(c->wf), d_wf,
+                  hw, total, (size_t)2 * hw, (size_t)hw);
+        c->launches++;
+    }
+    if (d_res) {
+        HN_LAUNCH(c2_to_nchw2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, reinterpret_cast<const float2*>(c->res), d_res,
+                  hw, total, (size_t)2 * hw, (size_t)hw);
+        c->launches++;
+    }
+    if (d_hflat) HN_TRY(copy_states_out(c, d_hflat, c->batch, st));
+    HN_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+int hn_get_states(hn_ctx* c, float* d_hflat, int batch, void* stream) {
+    if (!c || !d_hflat) return fail(HN_ERR_ARG, "NULL argument");
+    if (batch < 1 || batch > c->max_batch) return fail(HN_ERR_ARG, "batch out of range for this context");
+    HN_TRY(copy_states_out(c, d_hflat, batch, (cudaStream_t)stream));
+    HN_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+#ifndef HN_EMU
+static int get_graph(hn_ctx* c, int B, cudaGraphExec_t* out) {
+    const long long key = ((long long)B << 8) | ((long long)c->cur << 4) | (long long)c->engine;
+    auto it = c->graphs.find(key);
+    if (it != c->graphs.end()) {
+        *out = it->second;
+        return HN_OK;
+    }
+    cudaStream_t cs;
+    HN_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    const int64_t before = c->launches;
+    HN_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    int rc = launch_iteration(c, B, cs);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(cs, &g);
+    c->kernels_per_iter = (int)(c->launches - before);
+    c->launches = before;
+    if (rc != HN_OK) {
+        if (g) cudaGraphDestroy(g);
+        cudaStreamDestroy(cs);
+        return rc;
+    }
+    if (e != cudaSuccess) {
+        cudaStreamDestroy(cs);
+        return fail(HN_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(e));
+    }
+    cudaGraphExec_t ex = nullptr;
+    e = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    cudaStreamDestroy(cs);
+    if (e != cudaSuccess) return fail(HN_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    c->graphs[key] = ex;
+    *out = ex;
+    return HN_OK;
+}
+#endif
+
+int hn_run(hn_ctx* c, int n_iters, float* d_rmse, float* d_wf_hist, float* d_res_hist, float* d_h_hist, void* stream) {
+    if (!c) return fail(HN_ERR_ARG, "ctx is NULL");
+    if (!c->problem_set) return fail(HN_ERR_STATE, "no solve state: call hn_reset or hn_set_state first");
+    if (n_iters < 0) return fail(HN_ERR_ARG, "n_iters < 0");
+    if (n_iters == 0) return HN_OK;
+    HN_TRY(check_ready(c, c->batch));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = c->batch, hw = c->n * c->n;
+    const size_t need = (size_t)n_iters * B;
+    if (need > c->ssq_cap) {
+#ifndef HN_EMU
+        HN_CUDA(cudaStreamSynchronize(st));
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);   // graphs hold the old ssq pointer
+        c->graphs.clear();
+#endif
+        if (c->ssq) cudaFree(c->ssq);
+        c->ssq = nullptr;
+        size_t cap = need < 4096 ? 4096 : need;
+        HN_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->ssq), cap * sizeof(double)));
+        c->ssq_cap = cap;
+    }
+    HN_CUDA(cudaMemsetAsync(c->ssq, 0, need * sizeof(double), st));
+    HN_CUDA(cudaMemsetAsync(c->iter_dev, 0, sizeof(int), st));
+    const size_t total = (size_t)B * hw;
+    for (int it = 0; it < n_iters; it++) {
+#ifndef HN_EMU
+        if (c->use_graph) {
+            cudaGraphExec_t ex;
+            HN_TRY(get_graph(c, B, &ex));
+            HN_CUDA(cudaGraphLaunch(ex, st));
+            c->launches += c->kernels_per_iter;
+        } else
+#endif
+        {
+            const int64_t before = c->launches;
+            HN_TRY(launch_iteration(c, B, st));
+            c->kernels_per_iter = (int)(c->launches - before);
+        }
+        c->cur ^= 1;
+        if (d_wf_hist) {
+            HN_LAUNCH(c2_to_nchw2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, reinterpret_cast<const float2*>(c->wf),
+                      d_wf_hist + (size_t)it * total * 2, hw, total, (size_t)2 * hw, (size_t)hw);
+            c->launches++;
+        }
+        if (d_res_hist) {
+            HN_LAUNCH(c2_to_nchw2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, reinterpret_cast<const float2*>(c->res),
+                      d_res_hist + (size_t)it * total * 2, hw, total, (size_t)2 * hw, (size_t)hw);
+            c->launches++;
+        }
+        if (d_h_hist) HN_TRY(copy_states_out(c, d_h_hist + (size_t)it * B * 2 * c->state_len, B, st));
+    }
+    if (d_rmse) {
+        HN_LAUNCH(finalize_rmse_kernel, dim3(grid1d(need)), dim3(LAY_THREADS), 0, st, c->ssq, d_rmse, (int)need,
+                  1.0 / (2.0 * (double)hw));
+        c->launches++;
+    }
+    HN_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+int hn_residual(hn_ctx* c, const float* d_x, const float* d_ksq, float* d_out, float* d_rmse, int batch, void* stream) {
+    HN_TRY(check_ready(c, batch));
+    if (!d_x || !d_out) return fail(HN_ERR_ARG, "NULL argument");
+    if (!d_ksq && !(c->problem_set && c->batch == batch)) return fail(HN_ERR_STATE, "no k_sq in the context for this batch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int hw = c->n * c->n;
+    const size_t total = (size_t)batch * hw;
+    HN_LAUNCH(nchw2_to_c2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_x, reinterpret_cast<float2*>(c->tmp2), hw, total);
+    HN_CUDA(cudaMemsetAsync(c->ssq1, 0, (size_t)batch * sizeof(double), st));
+    HN_TRY(launch_spectral(c, batch, st, c->tmp2, d_ksq ? d_ksq : c->ksq, c->src, c->src_batch, c->tmp2b, c->ssq1, c->iter_dev + 1));
+    HN_LAUNCH(c2_to_nchw2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, reinterpret_cast<const float2*>(c->tmp2b), d_out, hw,
+              total, (size_t)2 * hw, (size_t)hw);
+    c->launches += 2;
+    if (d_rmse) {
+        HN_LAUNCH(finalize_rmse_kernel, dim3(1), dim3(LAY_THREADS), 0, st, c->ssq1, d_rmse, batch, 1.0 / (2.0 * (double)hw));
+        c->launches++;
+    }
+    HN_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+int hn_laplacian(hn_ctx* c, const float* d_x, float* d_out, int batch, void* stream) {
+    if (!c || !d_x || !d_out) return fail(HN_ERR_ARG, "NULL argument");
+    if (batch < 1 || batch > c->max_batch) return fail(HN_ERR_ARG, "batch out of range for this context");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int hw = c->n * c->n;
+    const size_t total = (size_t)batch * hw;
+    HN_LAUNCH(nchw2_to_c2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_x, reinterpret_cast<float2*>(c->tmp2), hw, total);
+    HN_TRY(launch_spectral(c, batch, st, c->tmp2, nullptr, nullptr, 1, c->tmp2b, nullptr, c->iter_dev + 1));
+    HN_LAUNCH(c2_to_nchw2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, reinterpret_cast<const float2*>(c->tmp2b), d_out, hw,
+              total, (size_t)2 * hw, (size_t)hw);
+    c->launches += 2;
+    HN_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+int hn_unet(hn_ctx* c, const float* d_in, float* d_out, int batch, void* stream) {
+    if (!c || !d_in || !d_out) return fail(HN_ERR_ARG, "NULL argument");
+    if (batch < 1 || batch > c->max_batch) return fail(HN_ERR_ARG, "batch out of range for this context");
+    if (!c->weights_set) return fail(HN_ERR_STATE, "hn_load_weights has not been called");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int hw = c->n * c->n;
+    const size_t total = (size_t)batch * hw;
+    HN_LAUNCH(nchw6_to_nhwc8_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_in, c->in6, hw, total);
+    c->launches++;
+    HN_TRY(launch_unet(c, batch, st, true, true));
+    c->cur ^= 1;
+    HN_LAUNCH(c2_to_nchw2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, reinterpret_cast<const float2*>(c->dwf), d_out, hw,
+              total, (size_t)2 * hw, (size_t)hw);
+    c->launches++;
+    HN_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+int hn_state_len(const hn_ctx* c) { return c ? c->state_len : HN_ERR_ARG; }
+int64_t hn_launch_count(const hn_ctx* c) { return c ? c->launches : 0; }
+int hn_kernels_per_iteration(const hn_ctx* c) { return c ? c->kernels_per_iter : HN_ERR_ARG; }
+
+int hn_debug_tensor(hn_ctx* c, const char* name, float* d_out, int batch, void* stream) {
+    if (!c || !name || !d_out) return fail(HN_ERR_ARG, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const std::string s(name);
+    const float* src = nullptr;
+    int r = 0;
+    auto lvl = [&](size_t pos) { return (s.size() > pos && s[pos] >= '0' && s[pos] <= '4') ? s[pos] - '0' : -1; };
+    if (s == "bot") { src = c->bot; r = c->r[kDepth]; }
+    else if (s.rfind("skip", 0) == 0 && lvl(4) >= 0 && lvl(4) < kDepth) { src = c->skip[lvl(4)]; r = c->r[lvl(4)]; }
+    else if (s.rfind("mid", 0) == 0 && lvl(3) >= 0) { src = c->mid[lvl(3)]; r = c->r[lvl(3)]; }
+    else if (s.rfind("up", 0) == 0 && lvl(2) >= 0 && lvl(2) < kDepth) { src = c->upo[lvl(2)]; r = c->r[lvl(2)]; }
+    else if (s.rfind("dec", 0) == 0 && lvl(3) >= 1 && lvl(3) < kDepth) { src = c->dec[lvl(3)]; r = c->r[lvl(3)]; }
+    else if (s.rfind("x", 0) == 0 && lvl(1) >= 0) { src = c->x[lvl(1)]; r = c->r[lvl(1)]; }
+    else return fail(HN_ERR_ARG, "unknown tensor name");
+    const size_t total = (size_t)batch * r * r;
+    HN_LAUNCH(nhwc8_to_nchw_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, src, d_out, r * r, total);
+    c->launches++;
+    HN_CUDA(cudaGetLastError());
+    return 8;
+}
+
+int hn_set_engine(hn_ctx* c, int engine) {
+    if (!c) return fail(HN_ERR_ARG, "ctx is NULL");
+    if (engine != 0) return fail(HN_ERR_ARG, "only engine 0 (fp32 CUDA-core) is available in this build");
+    c->engine = engine;
+    return c->engine;
+}
+
+int hn_profile_iteration(hn_ctx* c, float out_ms[2], void* stream) {
+    if (!c || !out_ms) return fail(HN_ERR_ARG, "NULL argument");
+    if (!c->problem_set) return fail(HN_ERR_STATE, "no solve state");
+    out_ms[0] = out_ms[1] = 0.f;
+#ifndef HN_EMU
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t e0, e1, e2;
+    HN_CUDA(cudaEventCreate(&e0));
+    HN_CUDA(cudaEventCreate(&e1));
+    HN_CUDA(cudaEventCreate(&e2));
+    HN_CUDA(cudaMemsetAsync(c->ssq1, 0, (size_t)c->batch * sizeof(double), st));
+    HN_CUDA(cudaEventRecord(e0, st));
+    int rc = launch_unet(c, c->batch, st, false, false);
+    if (rc == HN_OK) {
+        cudaEventRecord(e1, st);
+        rc = launch_spectral(c, c->batch, st, c->wf, c->ksq, c->src, c->src_batch, c->res, c->ssq1, c->iter_dev + 1);
+    }
+    if (rc == HN_OK) {
+        cudaEventRecord(e2, st);
+        cudaEventSynchronize(e2);
+        cudaEventElapsedTime(&out_ms[0], e0, e1);
+        cudaEventElapsedTime(&out_ms[1], e1, e2);
+        c->cur ^= 1;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    HN_TRY(rc);
+    HN_CUDA(cudaGetLastError());
+#endif
+    return HN_OK;
+}
+
+}  // extern "C"

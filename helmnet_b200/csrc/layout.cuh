@@ -1,0 +1,90 @@
+// layout.cuh -- boundary kernels: conversion between the reference's tensor layouts (NCHW, possibly
+// strided) and the solver's resident layouts (interleaved complex float2 / NHWC8), plus the solve setup
+// of IterativeSolver.get_initials (helmnet/hybridnet.py:522-538).  All are off the per-iteration path
+// except advance_iter_kernel (one thread) and the optional history snapshots.
+#pragma once
+#include "common.cuh"
+
+namespace hn {
+
+constexpr int LAY_THREADS = 256;
+
+// [B,2,H,W] -> float2 [B,H,W]
+__global__ void nchw2_to_c2_kernel(const float* __restrict__ in, float2* __restrict__ out, int hw, size_t total) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / hw, p = i - b * hw;
+        out[i] = make_float2(in[(b * 2) * hw + p], in[(b * 2 + 1) * hw + p]);
+    }
+}
+// float2 [B,H,W] -> [B,2,H,W] with an output batch stride (in floats) so that per-level hidden states can be
+// scattered into the flattened [B,2,S] layout of HybridNet.flatten_state (architectures.py:419-423).
+__global__ void c2_to_nchw2_kernel(const float2* __restrict__ in, float* __restrict__ out, int hw, size_t total,
+                                   size_t out_bstride, size_t out_cstride) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / hw, p = i - b * hw;
+        const float2 v = in[i];
+        out[b * out_bstride + p] = v.x;
+        out[b * out_bstride + out_cstride + p] = v.y;
+    }
+}
+// gather variant of the above: [B,2,*] with batch/channel strides -> float2 [B,hw]
+__global__ void nchw2_strided_to_c2_kernel(const float* __restrict__ in, float2* __restrict__ out, int hw, size_t total,
+                                           size_t in_bstride, size_t in_cstride) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / hw, p = i - b * hw;
+        out[i] = make_float2(in[b * in_bstride + p], in[b * in_bstride + in_cstride + p]);
+    }
+}
+// arbitrary 4-D strides (source maps arrive as permuted views, hybridnet.py:152,167)
+__global__ void src_strided_to_c2_kernel(const float* __restrict__ in, float2* __restrict__ out, int n, size_t total,
+                                         long long sb, long long sc, long long sh, long long sw) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / ((size_t)n * n), p = i - b * (size_t)n * n;
+        const long long y = (long long)(p / n), x = (long long)(p % n);
+        const long long o = (long long)b * sb + y * sh + x * sw;
+        out[i] = make_float2(in[o], in[o + sc]);
+    }
+}
+// get_initials + initial residual: k_sq = (omega/sos)^2, wf = 0, res = L(0) + k_sq*0 - source = -source
+__global__ void reset_kernel(const float* __restrict__ sos, float* __restrict__ ksq, float2* __restrict__ wf,
+                             float2* __restrict__ res, const float2* __restrict__ src, int src_batch, float omega, int hw,
+                             size_t total) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / hw, p = i - b * hw;
+        const float q = omega / sos[i];
+        ksq[i] = q * q;
+        wf[i] = make_float2(0.f, 0.f);
+        const float2 s = src[(src_batch > 1 ? b * hw : 0) + p];
+        res[i] = make_float2(0.f - s.x, 0.f - s.y);
+    }
+}
+// [B,6,H,W] -> NHWC8 (channels 6,7 zero): input of HybridNet.forward when called directly
+__global__ void nchw6_to_nhwc8_kernel(const float* __restrict__ in, float* __restrict__ out, int hw, size_t total) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / hw, p = i - b * hw;
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 6; c++) v[c] = in[(b * 6 + c) * hw + p];
+        v[6] = v[7] = 0.f;
+        float4* o = reinterpret_cast<float4*>(out + i * 8);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+// NHWC8 -> [B,8,H,W] (debug taps)
+__global__ void nhwc8_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int hw, size_t total) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / hw, p = i - b * hw;
+#pragma unroll
+        for (int c = 0; c < 8; c++) out[(b * 8 + c) * hw + p] = in[i * 8 + c];
+    }
+}
+__global__ void finalize_rmse_kernel(const double* __restrict__ ssq, float* __restrict__ rmse, int count, double inv_count) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+        rmse[i] = (float)sqrt(ssq[i] * inv_count);
+}
+__global__ void advance_iter_kernel(int* it) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *it += 1;
+}
+
+}  // namespace hn

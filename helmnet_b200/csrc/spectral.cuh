@@ -1,0 +1,228 @@
+// spectral.cuh -- pseudo-spectral Laplacian with PML + Helmholtz residual + per-sample residual norm.
+//
+// Reference semantics:
+//   helmnet/spectral.py:31-79   fast_laplacian_with_pml:  L u = ax*F^-1(i kx u^) + bx*F^-1(-kx^2 u^)
+//                                                             + ay*F^-1(i ky u^) + by*F^-1(-ky^2 u^)
+//   helmnet/hybridnet.py:544-556 get_residual:            r = L u + k_sq * u - source
+//   helmnet/hybridnet.py:295-297 test_loss_function:      rmse_b = sqrt(mean_{c,h,w} r^2)
+//
+// The reference evaluates L with one 2-D FFT and four 2-D inverse FFTs.  The 2-D transform is separable
+// and each term differentiates along ONE axis, so  F2^-1(i kx F2 u) == F_x^-1(i k F_x u)  exactly:
+// L u = R(u) + C(u) with R acting on whole rows and C on whole columns (the operator has
+// global support per axis, so a tile is a set of complete lines staged in shared memory -- there is no
+// halo).  Two kernels:
+//   spectral_rows_kernel : R(u) for L rows per CTA             -> rx
+//   spectral_cols_kernel : C(u) for CW columns per CTA, fused with  r = rx + C(u) + k_sq*u - source,
+//                          the store of r and the per-sample sum of squares (warp shuffles + one
+//                          double atomicAdd per CTA).
+// Line transforms are radix-4/2/generic Stockham FFTs in shared memory with twiddles computed in double
+// precision on the host; inverse transforms use conj(FFT(conj(.))) with the 1/N folded into the
+// spectral multipliers.
+#pragma once
+#include "common.cuh"
+
+namespace hn {
+
+constexpr int kMaxStages = 16;
+
+struct SpecTables {
+    const float2* tw;   // [n]  exp(-2 pi i k / n)
+    const float* mk;    // [n]  k_kappa / n              (k cast to float32 first, spectral.py:141)
+    const float* msq;   // [n]  -(k_kappa^2) / n         (k^2 in float32, spectral.py:281)
+    const float2* a;    // [n]  -gamma' / gamma^3        (spectral.py:334-337), zero outside the PML strips
+    const float2* b;    // [n]  1 / gamma^2
+    int n, pml, nstages;
+    int radix[kMaxStages];
+};
+
+// Forward FFT of `nl` lines of length n stored with pitch lp in x; y is scratch of the same shape.
+// Stockham autosort, decimation in frequency:  for stage length len = r*m and stride s,
+//   y[q + s*(r*p + j)] = ( sum_k x[q + s*(p + m*k)] * w_r^{jk} ) * w_len^{p*j},   p < m, q < s.
+// Returns the buffer holding the result.  Ends with a __syncthreads().
+__device__ inline float2* fft_lines(float2* x, float2* y, int nl, int lp, const float2* tw, const SpecTables& t) {
+    const int n = t.n;
+    int s = 1, len = n;
+    for (int st = 0; st < t.nstages; st++) {
+        const int r = t.radix[st];
+        const int m = len / r;
+        const int per_line = n / r;
+        const int items = nl * per_line;
+        for (int it = threadIdx.x; it < items; it += blockDim.x) {
+            const int l = it / per_line, idx = it - l * per_line;
+            const int p = idx / s, q = idx - p * s;
+            const float2* xi = x + l * lp + q + s * p;
+            float2* yo = y + l * lp + q + s * r * p;
+            const int sm = s * m;
+            if (r == 4) {
+                const float2 a0 = xi[0], a1 = xi[sm], a2 = xi[2 * sm], a3 = xi[3 * sm];
+                const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
+                const float2 b0 = cadd(t0, t2), b2 = csub(t0, t2);
+                const float2 b1 = make_float2(t1.x + t3.y, t1.y - t3.x);   // t1 - i t3
+                const float2 b3 = make_float2(t1.x - t3.y, t1.y + t3.x);   // t1 + i t3
+                const int tp = p * s;
+                yo[0] = b0;
+                yo[s] = cmul(b1, tw[tp]);
+                yo[2 * s] = cmul(b2, tw[2 * tp]);
+                yo[3 * s] = cmul(b3, tw[3 * tp]);
+            } else if (r == 2) {
+                const float2 a0 = xi[0], a1 = xi[sm];
+                yo[0] = cadd(a0, a1);
+                yo[s] = cmul(csub(a0, a1), tw[p * s]);
+            } else {
+                const int wr = n / r;
+                for (int j = 0; j < r; j++) {
+                    float2 acc = xi[0];
+                    for (int k = 1; k < r; k++) acc = cadd(acc, cmul(xi[k * sm], tw[((j * k) % r) * wr]));
+                    yo[j * s] = (j == 0) ? acc : cmul(acc, tw[p * s * j]);
+                }
+            }
+        }
+        __syncthreads();
+        float2* tmp = x;
+        x = y;
+        y = tmp;
+        len = m;
+        s *= r;
+    }
+    return x;
+}
+
+// One axis of the operator applied to `nl` lines held in buffer A (pitch lp):
+//   out_j = b_j * F^-1(-k^2 F u)_j + a_j * F^-1(i k F u)_j
+// Uses three line buffers A,B,C and a small strip buffer S[nl][2*pml]; returns the buffer holding
+// conj(F^-1(-k^2 u^)) (call it E) -- the caller finishes  b_j*conj(E_j) + strip term.
+__device__ inline float2* axis_operator(float2* A, float2* B, float2* C, float2* S, int nl, int lp, const float2* tw,
+                                        const SpecTables& t) {
+    const int n = t.n, pml = t.pml;
+    float2* F = fft_lines(A, B, nl, lp, tw, t);   // u^
+    float2* O = (F == A) ? B : A;
+    // first derivative (only its PML-strip samples are needed: a == 0 elsewhere)
+    if (pml > 0) {
+        for (int it = threadIdx.x; it < nl * n; it += blockDim.x) {
+            const int l = it / n, k = it - l * n;
+            const float2 v = F[l * lp + k];
+            const float mk = __ldg(t.mk + k);
+            O[l * lp + k] = make_float2(-mk * v.y, -mk * v.x);   // conj( (i k / n) * u^ )
+        }
+        __syncthreads();
+        float2* D = fft_lines(O, C, nl, lp, tw, t);
+        for (int it = threadIdx.x; it < nl * 2 * pml; it += blockDim.x) {
+            const int l = it / (2 * pml), mth = it - l * 2 * pml;
+            const int j = (mth < pml) ? mth : n - 2 * pml + mth;
+            S[it] = cmul(__ldg(t.a + j), cconj(D[l * lp + j]));
+        }
+        __syncthreads();
+    }
+    // second derivative
+    for (int it = threadIdx.x; it < nl * n; it += blockDim.x) {
+        const int l = it / n, k = it - l * n;
+        const float2 v = F[l * lp + k];
+        const float ms = __ldg(t.msq + k);
+        O[l * lp + k] = make_float2(ms * v.x, -ms * v.y);        // conj( (-k^2 / n) * u^ )
+    }
+    __syncthreads();
+    return fft_lines(O, C, nl, lp, tw, t);
+}
+
+__device__ __forceinline__ float2 axis_value(const float2* E, const float2* S, int l, int lp, int j, const SpecTables& t) {
+    float2 v = cmul(__ldg(t.b + j), cconj(E[l * lp + j]));
+    const int n = t.n, pml = t.pml;
+    if (j < pml) v = cadd(v, S[l * 2 * pml + j]);
+    else if (j >= n - pml) v = cadd(v, S[l * 2 * pml + j - (n - 2 * pml)]);
+    return v;
+}
+
+__host__ __device__ inline size_t spectral_smem_bytes(int n, int lines, int pml) {
+    return (size_t)n * 8 + (size_t)3 * lines * (n + 1) * 8 + (size_t)lines * 2 * (pml > 0 ? pml : 1) * 8;
+}
+
+constexpr int SPEC_THREADS = 256;
+
+__global__ void __launch_bounds__(SPEC_THREADS) spectral_rows_kernel(SpecTables t, const float2* __restrict__ u,
+                                                                     float2* __restrict__ rx, int total_rows, int L) {
+    HN_DYN_SMEM(float2, smem_sp);
+    const int n = t.n, lp = n + 1;
+    float2* tw = smem_sp;
+    float2* A = tw + n;
+    float2* B = A + L * lp;
+    float2* C = B + L * lp;
+    float2* S = C + L * lp;
+    const int row0 = blockIdx.x * L;
+    const int nl = min(L, total_rows - row0);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) tw[i] = __ldg(t.tw + i);
+    for (int it = threadIdx.x; it < nl * n; it += blockDim.x) {
+        const int l = it / n, j = it - l * n;
+        A[l * lp + j] = __ldg(u + (size_t)(row0 + l) * n + j);
+    }
+    __syncthreads();
+    const float2* E = axis_operator(A, B, C, S, nl, lp, tw, t);
+    for (int it = threadIdx.x; it < nl * n; it += blockDim.x) {
+        const int l = it / n, j = it - l * n;
+        rx[(size_t)(row0 + l) * n + j] = axis_value(E, S, l, lp, j, t);
+    }
+}
+
+struct ColsArgs {
+    const float2* u;      // [B][n][n]
+    const float2* rx;     // [B][n][n]  row-axis part
+    const float* ksq;     // [B][n][n] or null
+    const float2* src;    // [src_batch][n][n] or null
+    float2* res;          // [B][n][n]
+    double* ssq;          // [slots][B] or null
+    const int* slot;      // device scalar: which ssq slot (iteration index)
+    int src_batch, B, CW;
+};
+
+__global__ void __launch_bounds__(SPEC_THREADS) spectral_cols_kernel(SpecTables t, ColsArgs a) {
+    HN_DYN_SMEM(float2, smem_sp);
+    __shared__ float red[SPEC_THREADS / 32];
+    const int n = t.n, lp = n + 1, CW = a.CW;
+    float2* tw = smem_sp;
+    float2* A = tw + n;
+    float2* B = A + CW * lp;
+    float2* C = B + CW * lp;
+    float2* S = C + CW * lp;
+    const int b = blockIdx.y, j0 = blockIdx.x * CW;
+    const int nc = min(CW, n - j0);
+    const size_t img = (size_t)b * n * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) tw[i] = __ldg(t.tw + i);
+    for (int it = threadIdx.x; it < n * CW; it += blockDim.x) {
+        const int i = it / CW, c = it - i * CW;
+        if (c < nc) A[c * lp + i] = __ldg(a.u + img + (size_t)i * n + j0 + c);
+    }
+    __syncthreads();
+    const float2* E = axis_operator(A, B, C, S, nc, lp, tw, t);
+    float part = 0.f;
+    for (int it = threadIdx.x; it < n * CW; it += blockDim.x) {
+        const int i = it / CW, c = it - i * CW;
+        if (c >= nc) continue;
+        const size_t p = img + (size_t)i * n + j0 + c;
+        float2 r = cadd(__ldg(a.rx + p), axis_value(E, S, c, lp, i, t));
+        if (a.ksq != nullptr) {
+            const float kq = __ldg(a.ksq + p);
+            const float2 uu = __ldg(a.u + p);
+            r.x = fmaf(kq, uu.x, r.x);
+            r.y = fmaf(kq, uu.y, r.y);
+        }
+        if (a.src != nullptr) {
+            const float2 sv = __ldg(a.src + (a.src_batch > 1 ? img : (size_t)0) + (size_t)i * n + j0 + c);
+            r.x -= sv.x;
+            r.y -= sv.y;
+        }
+        a.res[p] = r;
+        part = fmaf(r.x, r.x, part);
+        part = fmaf(r.y, r.y, part);
+    }
+    if (a.ssq != nullptr) {
+        part = warp_sum(part);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tot = 0.f;
+            for (int w = 0; w < SPEC_THREADS / 32; w++) tot += red[w];
+            atomicAdd(a.ssq + (size_t)(*a.slot) * a.B + b, (double)tot);
+        }
+    }
+}
+
+}  // namespace hn

@@ -1,0 +1,525 @@
+"""Drop-in ``IterativeSolver`` for helmnet's inference path, backed by libhelmnet_sm100.so.
+
+API parity target: ``helmnet.IterativeSolver`` (reference helmnet/hybridnet.py) as used by README.md:58-83,
+examples/simple_scattering.py, evaluate.py and support_functions.fig_generic:
+
+    load_from_checkpoint / freeze / to / device / hparams / set_domain_size / forward / n_steps /
+    single_step / get_residual / apply_laplacian / get_initials / test_loss_function / set_laplacian /
+    setup_source / set_source_maps / set_source / reset_source / set_multiple_sources /
+    forward_variable_src / f.{state_dict, init_by_size, get_states, set_states, clear_states, ...}
+
+PyTorch is the host here (device memory, streams, parameter containers).  All arithmetic of the
+iteration -- UNet update, spectral Laplacian/PML residual, residual norm -- is enqueued through the C ABI on
+the caller's current CUDA stream.  No Lightning, no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import inspect
+import weakref
+from typing import List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .checkpoint import HParams, load_checkpoint
+from .source import SourceModule
+
+
+# --------------------------------------------------------------------------------------------------
+# parameter containers with the reference's state_dict names (helmnet/architectures.py:63-84, 186-252, 317-388)
+# --------------------------------------------------------------------------------------------------
+class DoubleConv(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.double_conv = nn.Sequential(
+            nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1),
+            nn.PReLU(),
+            nn.Conv2d(out_channels, out_channels, kernel_size=3, padding=1),
+        )
+
+
+class OutConv(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=1)
+
+
+class EncoderBlock(nn.Module):
+    """Weights of one encoder level + the Python-visible hidden state (``.state``)."""
+
+    def __init__(self, num_features: int, state_size: int = 2, domain_size: int = 0):
+        super().__init__()
+        self.state_size = state_size
+        self.num_features = num_features
+        self.domain_size = domain_size
+        self.use_state = True
+        self.conv_signal = DoubleConv(num_features + state_size, num_features)
+        self.down = nn.Conv2d(num_features, num_features, kernel_size=8, padding=3, stride=2)
+        self.conv_state = DoubleConv(num_features + state_size, state_size)
+        self.state: Optional[torch.Tensor] = None
+
+    def set_state(self, state):
+        self.state = state
+
+    def get_state(self):
+        return self.state
+
+    def clear_state(self, x):
+        self.state = torch.zeros([x.shape[0], 2, self.domain_size, self.domain_size], device=x.device)
+
+
+class HybridNet(nn.Module):
+    """The learned optimizer.  Holds the trained parameters; ``forward`` runs the CUDA UNet."""
+
+    def __init__(self, activation_function: str = "prelu", depth: int = 4, domain_size: int = 96, features: int = 8,
+                 inchannels: int = 6, state_channels: int = 2, state_depth: int = 4):
+        super().__init__()
+        if (activation_function.lower(), depth, features, inchannels, state_channels, state_depth) != ("prelu", 4, 8, 6, 2, 4):
+            raise NotImplementedError(
+                "libhelmnet_sm100 implements the shipped architecture only: prelu, depth=4, features=8, "
+                "inchannels=6, state_channels=2, state_depth=4")
+        self.activation_function = activation_function
+        self.depth, self.domain_size, self.features = depth, domain_size, features
+        self.inchannels, self.state_channels, self.state_depth = inchannels, state_channels, state_depth
+        self.init_by_size()
+        self.inc = DoubleConv(inchannels, features)
+        self.enc = nn.ModuleList([EncoderBlock(features, state_channels, self.states_dimension[d]) for d in range(depth)])
+        self.decode = nn.ModuleList([DoubleConv(features + features * (i < depth), features) for i in range(depth + 1)])
+        self.up = nn.ModuleList([nn.ConvTranspose2d(features, features, kernel_size=8, padding=3, output_padding=0, stride=2)
+                                 for _ in range(depth)])
+        self.outc = OutConv(features, 2)
+        self._owner = None  # weakref to the IterativeSolver that executes this net
+
+    # -- state packing (reference architectures.py:390-437) ------------------------------------------------
+    def init_by_size(self):
+        self.states_dimension = [self.domain_size // 2 ** d for d in range(self.depth)]
+        self.total_state_length = sum(s * s for s in self.states_dimension)
+        self.state_boundaries, start = [], 0
+        for s in self.states_dimension:
+            self.state_boundaries.append([start, start + s * s])
+            start += s * s
+
+    def get_states(self, flatten: bool = False):
+        h = [e.get_state() for e in self.enc]
+        return self.flatten_state(h) if flatten else h
+
+    def clear_states(self, x):
+        for e in self.enc:
+            e.clear_state(x)
+
+    def set_states(self, states, flatten: bool = False):
+        h = self.unflatten_state(states) if flatten else states
+        for e, s in zip(self.enc[: len(h)], h):
+            e.set_state(s)
+
+    def flatten_state(self, h_list):
+        return torch.cat([x.reshape(x.shape[0], x.shape[1], -1) for x in h_list], 2)
+
+    def unflatten_state(self, h_flatten):
+        b, c = h_flatten.shape[0], h_flatten.shape[1]
+        return [h_flatten[:, :, lo:hi].reshape(b, c, s, s) for (lo, hi), s in zip(self.state_boundaries, self.states_dimension)]
+
+    def weight_blob(self) -> torch.Tensor:
+        """The 48,160 parameters in state_dict order, the layout hn_load_weights expects."""
+        return torch.cat([v.detach().reshape(-1).float().cpu() for v in self.state_dict().values()]).contiguous()
+
+    def forward(self, x):
+        owner = self._owner() if self._owner is not None else None
+        if owner is None:
+            raise RuntimeError("HybridNet.forward needs its IterativeSolver (CUDA context owner)")
+        return owner._unet_forward(x)
+
+
+class SpectralLaplacian(nn.Module):
+    """``solver.Lap``: callable [B,H,W,2] -> [B,H,W,2] (reference spectral.py:246-262) + ``sigmas()``."""
+
+    def __init__(self, domain_size: int, PMLsize: int, k: float, sigma_max: float, owner=None):
+        super().__init__()
+        self.domain_size, self.PMLsize, self.k, self.sigma_max = domain_size, PMLsize, k, sigma_max
+        coord = np.arange(PMLsize)
+        prof = sigma_max * np.abs(1 - coord / PMLsize) ** 2 if PMLsize > 0 else np.zeros((0,))
+        sigma = np.zeros((domain_size,))
+        if PMLsize > 0:
+            sigma[:PMLsize] = prof
+            sigma[-PMLsize:] = prof[::-1]
+        sig = torch.tensor(sigma).float()
+        self.register_buffer("sigma_x", sig[None, :].repeat(domain_size, 1))   # varies along W
+        self.register_buffer("sigma_y", sig[:, None].repeat(1, domain_size))   # varies along H
+        self._owner = weakref.ref(owner) if owner is not None else None
+
+    def sigmas(self):
+        return self.sigma_x, self.sigma_y
+
+    def forward(self, x):
+        owner = self._owner() if self._owner is not None else None
+        if owner is None:
+            raise RuntimeError("SpectralLaplacian needs its IterativeSolver (CUDA context owner)")
+        return owner.apply_laplacian(x.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+
+
+# --------------------------------------------------------------------------------------------------
+class IterativeSolver(nn.Module):
+    def __init__(self, domain_size: int, k: float, omega: float, PMLsize: int, sigma_max: float, source_location: list,
+                 train_data_path: str = None, validation_data_path: str = None, test_data_path: str = None,
+                 activation_function: str = "relu", architecture: str = "custom_unet", gradient_clip_val: int = 0,
+                 batch_size: int = 24, buffer_size: int = 1000, depth: int = 4, features: int = 8,
+                 learning_rate: float = 1e-4, loss: str = "mse", minimum_learning_rate: float = 1e-4,
+                 optimizer: str = "adam", weight_decay: float = 0.0, max_iterations: int = 100,
+                 source_amplitude: int = 10, source_phase: int = 0, source_smoothing: bool = False,
+                 state_channels: int = 2, state_depth: int = 4, unrolling_steps: int = 10, _backend=None):
+        super().__init__()
+        frame = inspect.currentframe()
+        names = inspect.getargvalues(frame).args
+        self.hparams = HParams({n: frame.f_locals[n] for n in names if n not in ("self", "_backend")})
+        self._backend = _backend            # HelmnetLib, resolved lazily so that CPU-side construction works
+        self._ctx = None
+        self._ctx_key = None
+        self._ctx_max_batch = 0
+        self._weights_dirty = True
+        self._source_dirty = True
+        self.register_buffer("sigmas", None)
+        self.set_laplacian()
+        self.setup_source()
+        self.init_f()
+
+        def weights_init(m):
+            if isinstance(m, nn.Conv2d):
+                torch.nn.init.xavier_normal_(m.weight, gain=0.02)
+
+        self.f.apply(weights_init)
+
+    # ---- construction ----------------------------------------------------------------------------------
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, hparams_file=None, strict: bool = True, **kwargs):
+        ckpt = load_checkpoint(checkpoint_path, map_location="cpu")
+        hp = dict(ckpt["hyper_parameters"])
+        hp.update(kwargs)
+        accepted = set(inspect.signature(cls.__init__).parameters) - {"self"}
+        model = cls(**{k_: v for k_, v in hp.items() if k_ in accepted})
+        model.load_state_dict(ckpt["state_dict"], strict=strict)
+        if map_location is not None:
+            model.to(map_location)
+        return model
+
+    _DERIVED_PREFIXES = ("Lap.", "source_module.", "metric.", "replaybuffer.")
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        own = {k_ for k_ in self.state_dict().keys() if not k_.startswith(self._DERIVED_PREFIXES)}
+        own.discard("sigmas")
+        picked = {k_: v for k_, v in state_dict.items() if k_ in own}
+        missing = sorted(own - set(picked))
+        unexpected = sorted(k_ for k_ in state_dict if k_ not in own and not k_.startswith(self._DERIVED_PREFIXES) and k_ != "sigmas")
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict: missing {missing}, unexpected {unexpected}")
+        if "source" in picked and picked["source"].shape != self.source.shape:
+            self.source = nn.Parameter(picked.pop("source").clone(), requires_grad=False)
+        res = super().load_state_dict(picked, strict=False)
+        self._weights_dirty = True
+        self._source_dirty = True
+        return res
+
+    def init_f(self):
+        if self.hparams.architecture != "custom_unet":
+            raise NotImplementedError("Unknown architecture {}".format(self.hparams.architecture))
+        self.f = HybridNet(activation_function=self.hparams.activation_function, depth=self.hparams.depth,
+                           domain_size=self.hparams.domain_size, features=self.hparams.features, inchannels=6,
+                           state_channels=self.hparams.state_channels, state_depth=self.hparams.state_depth)
+        self.f._owner = weakref.ref(self)
+
+    @property
+    def device(self):
+        for p in self.parameters():
+            return p.device
+        return torch.device("cpu")
+
+    def freeze(self):
+        for p in self.parameters():
+            p.requires_grad = False
+        self.eval()
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._weights_dirty = True
+        self._source_dirty = True
+        return out
+
+    # ---- domain / operator / source setup (reference hybridnet.py:92-170) ------------------------------
+    def set_domain_size(self, domain_size, source_location=None, source_map=None):
+        self.hparams.domain_size = domain_size
+        self.f.domain_size = domain_size
+        self.set_laplacian()
+        self.setup_source()
+        self.Lap.to(self.device)
+        if self.source_module is not None:
+            self.source_module.to(self.device)
+        if source_location is not None:
+            self.set_multiple_sources([source_location])
+        else:
+            self.set_source_maps(source_map)
+        self.f.init_by_size()
+        for enc, size in zip(self.f.enc, self.f.states_dimension):
+            enc.domain_size = size
+
+    def set_laplacian(self):
+        self.Lap = SpectralLaplacian(self.hparams.domain_size, self.hparams.PMLsize, self.hparams.k, self.hparams.sigma_max,
+                                     owner=self)
+        sx, sy = self.Lap.sigmas()
+        self.sigmas = torch.stack([sx, sy]).float().to(self.device)
+        self._release_ctx()
+
+    def setup_source(self):
+        n, loc = self.hparams.domain_size, self.hparams.source_location
+        if not (0 <= loc[0] < n and 0 <= loc[1] < n):
+            # the reference raises IndexError here when the checkpoint's default location lies outside a
+            # smaller domain; the default map is overwritten by set_domain_size anyway, so use the centre.
+            loc = [n // 2, n // 2]
+        self.source_module = SourceModule(image_size=n, omega=self.hparams.omega, location=loc,
+                                          amplitude=self.hparams.source_amplitude, phase=self.hparams.source_phase,
+                                          smooth=self.hparams.source_smoothing).to(self.device)
+        with torch.no_grad():
+            self.set_source()
+
+    def set_source_maps(self, sourceval):
+        if sourceval is None:
+            raise ValueError("set_domain_size needs source_location or source_map")
+        self.source = nn.Parameter(sourceval.to(self.device), requires_grad=False)
+        self._source_dirty = True
+
+    def set_source(self):
+        self.set_source_maps(self.source_module.spatial_map(0).permute(0, 3, 1, 2))
+
+    def reset_source(self):
+        with torch.no_grad():
+            if not self.source_module.get_location() == self.hparams.source_location:
+                self.source_module.set_new_location(self.hparams.source_location)
+                self.set_source()
+
+    def set_multiple_sources(self, source_locations):
+        maps = []
+        with torch.no_grad():
+            for loc in source_locations:
+                self.source_module.set_new_location(loc)
+                maps.append(self.source_module.spatial_map(0).permute(0, 3, 1, 2))
+            self.set_source_maps(torch.cat(maps, 0))
+
+    # ---- CUDA context management -----------------------------------------------------------------------
+    @property
+    def lib(self):
+        if self._backend is None:
+            self._backend = _lib.default_lib()
+        return self._backend
+
+    def _release_ctx(self):
+        if getattr(self, "_ctx", None) is not None:
+            self.lib.hn_destroy(self._ctx)
+        self._ctx, self._ctx_key, self._ctx_max_batch = None, None, 0
+
+    def __del__(self):
+        try:
+            self._release_ctx()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(self.lib.stream_for(self.device)) if self.lib.requires_cuda else C.c_void_p(0)
+
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]):
+        return C.c_void_p(0 if t is None else t.data_ptr())
+
+    def _prep(self, t: torch.Tensor, name: str) -> torch.Tensor:
+        t = t.detach()
+        if t.device != self.device:
+            t = t.to(self.device)
+        self.lib.check_tensor(t, name)
+        return t.float().contiguous()
+
+    def _ensure_ctx(self, batch: int):
+        lib, dev = self.lib, self.device
+        if lib.requires_cuda and dev.type != "cuda":
+            raise _lib.HelmnetError("IterativeSolver is on the CPU: call solver.to('cuda:0'); there is no CPU path")
+        hp = self.hparams
+        key = (str(dev), int(hp.domain_size), int(hp.PMLsize), float(hp.sigma_max), float(hp.k), float(hp.omega))
+        if self._ctx is None or key != self._ctx_key or batch > self._ctx_max_batch:
+            self._release_ctx()
+            max_batch = max(batch, 1)
+            ctx = C.c_void_p()
+            idx = dev.index if dev.index is not None else (torch.cuda.current_device() if dev.type == "cuda" else 0)
+            lib.check(lib.hn_create(C.byref(ctx), idx, hp.domain_size, max_batch, hp.PMLsize, float(hp.sigma_max),
+                                    float(hp.k), float(hp.omega)), "hn_create")
+            self._ctx, self._ctx_key, self._ctx_max_batch = ctx, key, max_batch
+            self._weights_dirty = self._source_dirty = True
+        if self._weights_dirty:
+            blob = self.f.weight_blob()
+            lib.check(lib.hn_load_weights(self._ctx, self._ptr(blob), blob.numel()), "hn_load_weights")
+            self._weights_dirty = False
+        if self._source_dirty:
+            src = self.source.detach()
+            if src.device != dev:
+                src = src.to(dev)
+            if src.dtype != torch.float32:
+                src = src.float()
+            n = hp.domain_size
+            if src.dim() != 4 or src.shape[1] != 2 or src.shape[2] != n or src.shape[3] != n:
+                raise ValueError(f"source must be [S,2,{n},{n}], got {tuple(src.shape)}")
+            lib.check_tensor(src, "source")
+            strides = (C.c_int64 * 4)(*src.stride())
+            lib.check(lib.hn_set_source(self._ctx, self._ptr(src), src.shape[0], strides, self._stream()), "hn_set_source")
+            self._source_keepalive = src
+            self._source_dirty = False
+        return self._ctx
+
+    def sync_weights(self):
+        """Call after mutating ``solver.f`` parameters in place."""
+        self._weights_dirty = True
+
+    # ---- reference API: pieces of the loop -----------------------------------------------------------------
+    @staticmethod
+    def test_loss_function(x):
+        return x.pow(2).mean((1, 2, 3)).sqrt()
+
+    def get_initials(self, sos_maps: torch.Tensor):
+        k_sq = (self.hparams.omega / sos_maps) ** 2
+        wavefield = torch.zeros(k_sq.shape[0], 2, k_sq.shape[2], k_sq.shape[3], device=k_sq.device)
+        return k_sq, wavefield
+
+    def apply_laplacian(self, x: torch.Tensor):
+        x = self._prep(x, "x")
+        ctx = self._ensure_ctx(x.shape[0])
+        out = torch.empty_like(x)
+        self.lib.check(self.lib.hn_laplacian(ctx, self._ptr(x), self._ptr(out), x.shape[0], self._stream()), "hn_laplacian")
+        return out
+
+    def get_residual(self, x: torch.Tensor, k_sq: torch.Tensor):
+        x = self._prep(x, "x")
+        k_sq = self._prep(k_sq, "k_sq")
+        ctx = self._ensure_ctx(x.shape[0])
+        out = torch.empty_like(x)
+        self.lib.check(self.lib.hn_residual(ctx, self._ptr(x), self._ptr(k_sq), self._ptr(out), self._ptr(None), x.shape[0],
+                                            self._stream()), "hn_residual")
+        return out
+
+    def _push_states(self, ctx, batch):
+        hs = self.f.get_states()
+        if any(h is None for h in hs):
+            raise ValueError("You must set or clear the state before using this module")
+        flat = self._prep(self.f.flatten_state(hs), "state")
+        if flat.shape[0] != batch:
+            raise ValueError("hidden state batch does not match the input batch")
+        return flat
+
+    def _pull_states(self, ctx, batch):
+        flat = torch.empty(batch, 2, self.f.total_state_length, device=self.device)
+        self.lib.check(self.lib.hn_get(ctx, self._ptr(None), self._ptr(None), self._ptr(flat), self._stream()), "hn_get")
+        self.f.set_states(flat, flatten=True)
+
+    def _unet_forward(self, x: torch.Tensor):
+        x = self._prep(x, "input")
+        b = x.shape[0]
+        ctx = self._ensure_ctx(b)
+        flat = self._push_states(ctx, b)
+        lib = self.lib
+        lib.check(lib.hn_set_state(ctx, self._ptr(None), self._ptr(None), self._ptr(None), self._ptr(flat), b, self._stream()),
+                  "hn_set_state")
+        out = torch.empty(b, 2, x.shape[2], x.shape[3], device=self.device)
+        lib.check(lib.hn_unet(ctx, self._ptr(x), self._ptr(out), b, self._stream()), "hn_unet")
+        flat2 = torch.empty_like(flat)
+        lib.check(lib.hn_get_states(ctx, self._ptr(flat2), b, self._stream()), "hn_get_states")
+        self.f.set_states(flat2, flatten=True)
+        return out
+
+    def _run(self, ctx, batch, num_iterations, return_wavefields, return_states, return_residuals):
+        n, dev, lib = self.hparams.domain_size, self.device, self.lib
+        k_it = int(num_iterations)
+        rmse = torch.empty(k_it, batch, device=dev)
+        wf_hist = torch.empty(k_it, batch, 2, n, n, device=dev) if return_wavefields else None
+        res_hist = torch.empty(k_it, batch, 2, n, n, device=dev) if return_residuals else None
+        h_hist = torch.empty(k_it, batch, 2, self.f.total_state_length, device=dev) if return_states else None
+        lib.check(lib.hn_run(ctx, k_it, self._ptr(rmse), self._ptr(wf_hist), self._ptr(res_hist), self._ptr(h_hist),
+                             self._stream()), "hn_run")
+        return rmse, wf_hist, res_hist, h_hist
+
+    def _collect(self, ctx, batch, rmse, wf_hist, res_hist, h_hist, last_iteration):
+        n, dev, lib = self.hparams.domain_size, self.device, self.lib
+        wf_last = None if wf_hist is not None else torch.empty(batch, 2, n, n, device=dev)
+        res_last = None if res_hist is not None else torch.empty(batch, 2, n, n, device=dev)
+        flat = torch.empty(batch, 2, self.f.total_state_length, device=dev)
+        lib.check(lib.hn_get(ctx, self._ptr(wf_last), self._ptr(res_last), self._ptr(flat), self._stream()), "hn_get")
+        self.f.set_states(flat, flatten=True)
+        return {
+            "wavefields": list(wf_hist.unbind(0)) if wf_hist is not None else [wf_last],
+            "residuals": list(res_hist.unbind(0)) if res_hist is not None else [res_last],
+            "states": list(h_hist.unbind(0)) if h_hist is not None else [],
+            "last_iteration": last_iteration,
+            "residual_rmse": rmse,
+        }
+
+    def single_step(self, wavefield, k_sq, residual, get_residual: bool = True):
+        out = self.n_steps(wavefield, k_sq, residual, 1)
+        if get_residual:
+            return out["wavefields"][0], out["residuals"][0]
+        return out["wavefields"][0]
+
+    def n_steps(self, wavefield, k_sq, residual, num_iterations, return_wavefields=False, return_states=False,
+                return_residuals=True):
+        if num_iterations < 1:
+            raise ValueError("num_iterations must be >= 1")
+        wavefield, k_sq, residual = self._prep(wavefield, "wavefield"), self._prep(k_sq, "k_sq"), self._prep(residual, "residual")
+        b = wavefield.shape[0]
+        ctx = self._ensure_ctx(b)
+        flat = self._push_states(ctx, b)
+        self.lib.check(self.lib.hn_set_state(ctx, self._ptr(wavefield), self._ptr(residual), self._ptr(k_sq), self._ptr(flat), b,
+                                             self._stream()), "hn_set_state")
+        hist = self._run(ctx, b, num_iterations, return_wavefields, return_states, return_residuals)
+        return self._collect(ctx, b, *hist, last_iteration=num_iterations - 1)
+
+    def forward(self, sos_maps, return_wavefields=False, return_states=False, num_iterations=None, stop_if_diverge=False,
+                return_residuals=True):
+        """Reference hybridnet.py:654-697.  ``residuals`` is the per-iteration list of residual tensors as in
+        the reference; pass ``return_residuals=False`` for large runs to keep only the last one --
+        ``residual_rmse`` ([iterations, batch], the test_loss_function of every residual) is always returned."""
+        if num_iterations is None:
+            num_iterations = self.hparams.max_iterations
+        if num_iterations < 1:
+            raise ValueError("num_iterations must be >= 1")
+        sos = self._prep(sos_maps, "sos_maps")
+        n = self.hparams.domain_size
+        if sos.dim() != 4 or sos.shape[1] != 1 or sos.shape[2] != n or sos.shape[3] != n:
+            raise ValueError(f"sos_maps must be [B,1,{n},{n}], got {tuple(sos.shape)}")
+        b = sos.shape[0]
+        ctx = self._ensure_ctx(b)
+        self.lib.check(self.lib.hn_reset(ctx, self._ptr(sos), b, self._stream()), "hn_reset")
+        hist = self._run(ctx, b, num_iterations, return_wavefields, return_states, return_residuals)
+        return self._collect(ctx, b, *hist, last_iteration=num_iterations - 1)
+
+    def forward_variable_src(self, sos_maps, src_time_pairs, return_wavefields=False, return_states=False,
+                             num_iterations=None, stop_if_diverge=False, return_residuals=True):
+        """Reference hybridnet.py:699-754: swap the source map at given iterations and recompute the residual."""
+        if num_iterations is None:
+            num_iterations = self.hparams.max_iterations
+        times = sorted(set(int(t) for t in src_time_pairs["iteration"] if 0 <= int(t) < num_iterations))
+        src_maps = iter(src_time_pairs["src_maps"])
+        sos = self._prep(sos_maps, "sos_maps")
+        b, n, dev, lib = sos.shape[0], self.hparams.domain_size, self.device, self.lib
+        ctx = self._ensure_ctx(b)
+        lib.check(lib.hn_reset(ctx, self._ptr(sos), b, self._stream()), "hn_reset")
+        cuts = sorted(set([0] + times + [num_iterations]))
+        parts = []
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            if lo in times:
+                self.set_source_maps(next(src_maps))
+                ctx = self._ensure_ctx(b)
+                wf = torch.empty(b, 2, n, n, device=dev)
+                lib.check(lib.hn_get(ctx, self._ptr(wf), self._ptr(None), self._ptr(None), self._stream()), "hn_get")
+                res = torch.empty_like(wf)
+                lib.check(lib.hn_residual(ctx, self._ptr(wf), self._ptr(None), self._ptr(res), self._ptr(None), b, self._stream()),
+                          "hn_residual")
+                lib.check(lib.hn_set_state(ctx, self._ptr(None), self._ptr(res), self._ptr(None), self._ptr(None), b, self._stream()),
+                          "hn_set_state")
+            if hi > lo:
+                parts.append(self._run(ctx, b, hi - lo, return_wavefields, return_states, return_residuals))
+        cat = [torch.cat([p[i] for p in parts], 0) if parts[0][i] is not None else None for i in range(4)]
+        return self._collect(ctx, b, *cat, last_iteration=num_iterations - 1)

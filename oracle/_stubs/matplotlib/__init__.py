@@ -1,0 +1,2 @@
+def use(*a, **k):
+    pass
