@@ -211,7 +211,8 @@ class IterativeSolver(nn.Module):
         own.discard("sigmas")
         picked = {k_: v for k_, v in state_dict.items() if k_ in own}
         missing = sorted(own - set(picked))
-        unexpected = sorted(k_ for k_ in state_dict if k_ not in own and not k_.startswith(self._DERIVED_PREFIXES) and k_ != "sigmas")
+        full = set(self.state_dict().keys()) | {"sigmas"}
+        unexpected = sorted(k_ for k_ in state_dict if k_ not in full)   # e.g. the stale Lap.gamma_x of the shipped ckpt
         if strict and (missing or unexpected):
             raise RuntimeError(f"Error(s) in loading state_dict: missing {missing}, unexpected {unexpected}")
         if "source" in picked and picked["source"].shape != self.source.shape:

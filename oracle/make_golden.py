@@ -32,7 +32,7 @@ sys.path.insert(1, REF)
 sys.path.insert(2, os.path.dirname(HERE))
 
 from helmnet import IterativeSolver  # noqa: E402  (the reference)
-from oracle.helmnet_oracle import synthetic_sos  # noqa: E402  (input generator only)
+from helmnet_b200.synthetic import synthetic_sos  # noqa: E402  (input generator only)
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 CKPT = os.path.join(REF, "trained_models", "jcp_paper_trained_weights.ckpt")

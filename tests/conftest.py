@@ -1,0 +1,57 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+CKPT = os.path.join(GOLD, "jcp_paper_trained_weights_slim.ckpt")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+def rel_l2(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.fixture(scope="session")
+def gold():
+    def load(name):
+        return {k: v for k, v in np.load(os.path.join(GOLD, name)).items()}
+    return load
+
+
+@pytest.fixture(scope="session")
+def f_weights():
+    from helmnet_b200.checkpoint import load_checkpoint
+    sd = load_checkpoint(CKPT)["state_dict"]
+    return {k[2:]: v for k, v in sd.items() if k.startswith("f.")}
+
+
+@pytest.fixture(scope="session")
+def cuda_solver():
+    """IterativeSolver on cuda:0 through the product library (fails loudly if it is missing)."""
+    from helmnet_b200 import IterativeSolver
+    s = IterativeSolver.load_from_checkpoint(CKPT, strict=False, test_data_path=None)
+    s.freeze()
+    s.to("cuda:0")
+    return s
+
+
+@pytest.fixture(scope="session")
+def emu_solver():
+    """Same host code, kernels executed by the CPU fiber emulator (tests/emu) -- logic tests only."""
+    from emu_backend import EmuLib
+    from helmnet_b200 import IterativeSolver
+    s = IterativeSolver.load_from_checkpoint(CKPT, strict=False, test_data_path=None, _backend=EmuLib())
+    s.freeze()
+    return s

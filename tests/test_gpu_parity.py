@@ -1,0 +1,174 @@
+"""Parity tests proper: the CUDA path (through the C ABI) vs golden vectors of the unmodified reference and
+vs the CPU oracle on seeded inputs.  Tolerances are BASELINE.json's: per-iteration wavefield rel-L2 <= 1e-5,
+final wavefield <= 1e-3, residual-norm trajectory within the same bounds."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+PER_ITER_TOL = 1e-5
+FINAL_TOL = 1e-3
+
+
+def test_library_is_the_cuda_one(cuda_solver):
+    assert "sm_100a" in cuda_solver.lib.version() and cuda_solver.lib.requires_cuda
+    assert cuda_solver.device.type == "cuda"
+
+
+@pytest.mark.parametrize("n", [32, 96])
+def test_laplacian_kat(cuda_solver, gold, n):
+    g = gold(f"operator_n{n}.npz")
+    cuda_solver.set_domain_size(n, source_location=[n // 3, n // 2])
+    Lu = cuda_solver.Lap(torch.tensor(g["u"]).cuda())
+    assert rel_l2(Lu, g["Lu"]) < 1e-6
+    assert torch.equal(cuda_solver.source.cpu(), torch.tensor(g["source"])) or rel_l2(cuda_solver.source, g["source"]) < 1e-6
+
+
+@pytest.mark.parametrize("n", [48, 80, 256, 512, 1024])
+def test_laplacian_vs_oracle(cuda_solver, n):
+    from oracle import helmnet_oracle as O
+    cuda_solver.set_domain_size(n, source_location=[3, 4])
+    u = torch.randn(2, n, n, 2, generator=torch.Generator().manual_seed(n))
+    ref = O.laplacian(u, O.make_operator(n, 8, 2.0, 1.0))
+    assert rel_l2(cuda_solver.Lap(u.cuda()), ref) < 1e-6
+    # linearity (size independent property)
+    v = torch.randn(2, n, n, 2, generator=torch.Generator().manual_seed(n + 1)).cuda()
+    a = cuda_solver.Lap(u.cuda() + 2 * v)
+    b = cuda_solver.Lap(u.cuda()) + 2 * cuda_solver.Lap(v)
+    assert rel_l2(a, b) < 1e-5
+
+
+def test_unet_and_single_step_kat(cuda_solver, gold):
+    g = gold("unet_step_n32.npz")
+    s = cuda_solver
+    s.set_domain_size(32, source_location=[10, 16])
+    c = lambda k: torch.tensor(g[k]).cuda()
+    s.f.set_states(c("states_flat"), flatten=True)
+    d = s.f(c("inp"))
+    assert rel_l2(d, g["d_wf"]) < PER_ITER_TOL
+    assert rel_l2(s.f.get_states(flatten=True), g["states_flat_out"]) < PER_ITER_TOL
+    s.f.set_states(c("states_flat"), flatten=True)
+    up, res = s.single_step(c("wf"), c("k_sq"), c("res"))
+    assert rel_l2(up, g["up_wf"]) < PER_ITER_TOL and rel_l2(res, g["new_res"]) < 1e-4
+    assert rel_l2(s.get_residual(c("wf"), c("k_sq")), g["residual_of_wf"]) < 1e-6
+
+
+def test_layers_vs_torch_fp32(cuda_solver, f_weights):
+    """Every intermediate activation against plain PyTorch fp32 ops of the same layers (CPU)."""
+    import torch.nn.functional as F
+    import ctypes as C
+    from oracle import helmnet_oracle as O
+    s, n, b = cuda_solver, 96, 2
+    s.set_domain_size(n, source_location=[20, 30])
+    g = torch.Generator().manual_seed(11)
+    inp = torch.randn(b, 6, n, n, generator=g)
+    states = [torch.randn(b, 2, n >> d, n >> d, generator=g) * 0.3 for d in range(4)]
+    s.f.set_states(O.flatten_states(states).cuda(), flatten=True)
+    out = s.f(inp.cuda())
+    w = f_weights
+    ref = {}
+    x = O.double_conv(inp, w, "inc"); ref["x0"] = x
+    for d in range(4):
+        o = O.double_conv(torch.cat([x, states[d]], 1), w, f"enc.{d}.conv_signal"); ref[f"skip{d}"] = o
+        x = F.conv2d(o, w[f"enc.{d}.down.weight"], w[f"enc.{d}.down.bias"], stride=2, padding=3); ref[f"x{d+1}"] = x
+    x = O.double_conv(x, w, "decode.4"); ref["bot"] = x
+    for d in (3, 2, 1):
+        u = F.conv_transpose2d(x, w[f"up.{d}.weight"], w[f"up.{d}.bias"], stride=2, padding=3); ref[f"up{d}"] = u
+        x = O.double_conv(torch.cat([u, ref[f"skip{d}"]], 1), w, f"decode.{d}"); ref[f"dec{d}"] = x
+    ref["up0"] = F.conv_transpose2d(x, w["up.0.weight"], w["up.0.bias"], stride=2, padding=3)
+    worst = {}
+    for name, t in ref.items():
+        buf = torch.empty_like(t).cuda()
+        rc = s.lib.hn_debug_tensor(s._ctx, name.encode(), C.c_void_p(buf.data_ptr()), b, s._stream())
+        assert rc == 8, (name, s.lib.last_error())
+        worst[name] = rel_l2(buf, t)
+    full, _ = O.unet_forward(w, inp, states)
+    worst["out"] = rel_l2(out, full)
+    bad = {k: v for k, v in worst.items() if v > 5e-6}
+    assert not bad, f"layers off: {bad}  (all: {worst})"
+
+
+def test_trajectory_n96_golden(cuda_solver, gold):
+    g = gold("traj_n96_b2.npz")
+    s = cuda_solver
+    s.set_domain_size(96, source_location=[82, 48])
+    out = s.forward(torch.tensor(g["sos"]).cuda(), num_iterations=40, return_wavefields=True, return_states=True)
+    assert rel_l2(out["residual_rmse"], g["rmse"]) < PER_ITER_TOL
+    for i, k in enumerate(g["keep"]):
+        assert rel_l2(out["wavefields"][k], g["wavefields"][i]) < PER_ITER_TOL, k
+    assert rel_l2(out["states"][-1], g["states_last"]) < 1e-4
+    per_it = torch.stack([s.test_loss_function(r) for r in out["residuals"]])
+    assert rel_l2(per_it, out["residual_rmse"]) < 1e-5      # fused norm == test_loss_function of the stored residual
+
+
+def test_trajectory_readme_golden(cuda_solver, gold):
+    """README.md:62-70 lens example, 120 iterations (config[0] of BASELINE.json)."""
+    g = gold("traj_readme_n256.npz")
+    s = cuda_solver
+    n = 256
+    sos = np.ones((n, n)); sos[100:170, 30:240] = np.tile(np.linspace(2, 1, 210), (70, 1))
+    s.set_domain_size(n, source_location=[30, 128])
+    out = s.forward(torch.tensor(sos).float()[None, None].cuda(), num_iterations=120, return_wavefields=True)
+    rm = out["residual_rmse"].cpu().numpy()[:, 0]
+    assert np.max(np.abs(rm - g["rmse"][:, 0]) / g["rmse"][:, 0]) < 1e-4
+    assert int(np.argmax(rm < 1e-3)) == 52                   # first iteration with residual RMSE < 1e-3
+    for i, k in enumerate(g["keep"]):
+        e = rel_l2(out["wavefields"][k], g["wavefields"][i])
+        assert e < (PER_ITER_TOL if k < 100 else FINAL_TOL), (k, e)
+
+
+def test_trajectory_source_maps_golden(cuda_solver, gold):
+    g = gold("traj_srcmap_n64.npz")
+    s = cuda_solver
+    s.set_domain_size(64, source_map=torch.tensor(g["source"]).cuda())
+    out = s.forward(torch.tensor(g["sos"]).cuda(), num_iterations=30)
+    assert rel_l2(out["residual_rmse"], g["rmse"]) < PER_ITER_TOL
+    assert rel_l2(out["wavefields"][0], g["wavefield"]) < PER_ITER_TOL
+
+
+@pytest.mark.parametrize("n,b,iters", [(96, 32, 25), (48, 3, 10), (112, 2, 6), (512, 2, 6)])
+def test_forward_vs_oracle(cuda_solver, f_weights, n, b, iters):
+    """Seeded synthetic maps (config[1] shape 96^2 x 32 included), per-iteration bar at every iteration."""
+    from helmnet_b200.synthetic import synthetic_sos
+    from oracle import helmnet_oracle as O
+    s = cuda_solver
+    loc = [int(0.85 * n), n // 2]
+    s.set_domain_size(n, source_location=loc)
+    sos = synthetic_sos(b, n, seed=5)
+    orc = O.Oracle(f_weights, n)
+    orc.set_source(O.point_source(n, loc))
+    ref = orc.forward(sos, iters, keep_wavefields=True)
+    out = s.forward(sos.cuda(), num_iterations=iters, return_wavefields=True)
+    errs = [rel_l2(out["wavefields"][k], ref["wavefields"][k]) for k in range(iters)]
+    assert max(errs) < PER_ITER_TOL, errs
+    assert rel_l2(out["residual_rmse"], ref["rmse"]) < PER_ITER_TOL
+
+
+def test_full_size_properties(cuda_solver):
+    """BASELINE config 256^2 at a large batch: size-independent properties instead of an oracle run --
+    batch independence (sample i of a big batch == the same sample solved alone) and graph replay determinism."""
+    from helmnet_b200.synthetic import synthetic_sos
+    s, n, b = cuda_solver, 256, 64
+    s.set_domain_size(n, source_location=[30, 128])
+    sos = synthetic_sos(4, n, seed=9).repeat(b // 4, 1, 1, 1).cuda()
+    a = s.forward(sos, num_iterations=8)
+    a_wf, a_rm = a["wavefields"][0].clone(), a["residual_rmse"].clone()
+    again = s.forward(sos, num_iterations=8)
+    assert torch.equal(again["wavefields"][0], a_wf)
+    assert rel_l2(again["residual_rmse"], a_rm) < 1e-6
+    one = s.forward(sos[5:6], num_iterations=8)
+    assert torch.equal(one["wavefields"][0][0], a_wf[5])
+    assert torch.equal(a_wf[1], a_wf[5])                 # identical inputs at different batch slots
+
+
+def test_launch_accounting(cuda_solver):
+    s = cuda_solver
+    s.set_domain_size(64, source_location=[5, 5])
+    s.forward(torch.ones(1, 1, 64, 64).cuda(), num_iterations=3)
+    k = s.lib.hn_kernels_per_iteration(s._ctx)
+    assert 30 <= k <= 60
+    before = s.lib.hn_launch_count(s._ctx)
+    s.forward(torch.ones(1, 1, 64, 64).cuda(), num_iterations=5, return_residuals=False)
+    assert s.lib.hn_launch_count(s._ctx) - before >= 5 * k
