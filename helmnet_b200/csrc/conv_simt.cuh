@@ -48,6 +48,8 @@ struct Conv3Args {
     const float* bo;      // EPI_OUTC: outc bias [2]
     float* wf;            // EPI_OUTC: wavefield float2 [B][H][W], updated in place
     float* dwf_out;       // EPI_OUTC: when non-null store the raw network output here instead
+    const void* tc_bmat;  // tcgen05 engine only: fp16 split-weight image of this layer (unused by the SIMT kernel)
+    float tc_inv;         // tcgen05 engine only: 2^-kw
     int H, W;
 };
 

@@ -21,6 +21,10 @@
 #include "conv_simt.cuh"
 #include "layout.cuh"
 #include "spectral.cuh"
+#ifndef HN_EMU
+#include "conv_tc.cuh"
+#define HN_HAVE_TC 1
+#endif
 
 using namespace hn;
 
@@ -45,6 +49,8 @@ static int fail(int code, const std::string& msg) {
 
 struct ConvW {      // offsets (in floats) into the packed device blob
     size_t w = 0, b = 0, slope = 0;
+    size_t tc = (size_t)-1;   // offset (in halfs) of the tcgen05 B-operand image, C_out = 8 layers only
+    float tc_inv = 1.f;       // 2^-kw, inverse of the layer's weight block scale
 };
 struct Weights {
     ConvW inc[2], sig[kDepth][2], sta[kDepth][2], down[kDepth], bot[2], up[kDepth], dec[kDepth][2], outc;
@@ -80,6 +86,9 @@ struct hn_ctx {
     int rows_L = 1, cols_CW = 1;
     // weights
     float* wdev = nullptr;
+    uint16_t* tcw = nullptr;   // fp16 split-weight images for the tcgen05 convolutions
+    int* err_flag = nullptr;   // device watchdog flag of the tcgen05 kernels
+    int tc_min_res = 16;       // use the tensor-core kernels for levels with resolution >= this
     Weights W;
     // residual norms
     double* ssq = nullptr;
@@ -207,6 +216,7 @@ static int build_tables(hn_ctx* c) {
 // ------------------------------------------------------------------------------------------------
 struct Packer {
     std::vector<float> blob;
+    std::vector<uint16_t> halfs;   // tcgen05 B images
     size_t reserve(size_t nfl) {
         size_t off = (blob.size() + 3) & ~(size_t)3;
         blob.resize(off + nfl, 0.f);
@@ -257,6 +267,42 @@ static size_t pack_vec(Packer& pk, const float* v, int nfl) {
     return off;
 }
 
+#ifdef HN_HAVE_TC
+// W[co][ci][3][3] (co = 8) -> per (channel group g, tap) a 16 x 16 fp16 B operand in the canonical K-major
+// SWIZZLE_NONE layout:  byte(n,k) = (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2  with
+//   n <  8 (g1 = hi*W_hi):            k < 8: W_hi[co=n][ci=k]      k >= 8: 0
+//   n >= 8 (g2 = hi*W_lo + lo*W_hi):  k < 8: W_lo[co=n-8][ci=k]    k >= 8: W_hi[co=n-8][ci=k-8]
+// W' = W * 2^kw with max|W'| in [2^9, 2^10);  W_hi = fp16(W'),  W_lo = fp16((W' - W_hi) * 2^11).
+static void pack_tc(Packer& pk, const float* w, int cin, ConvW& out) {
+    const int G = (cin + 7) / 8;
+    float mx = 0.f;
+    for (int i = 0; i < 8 * cin * 9; i++) mx = fmaxf(mx, fabsf(w[i]));
+    int ex = 0;
+    if (mx > 0.f) frexpf(mx, &ex);
+    const int kw = 10 - ex;
+    const float scale = ldexpf(1.f, kw);
+    out.tc_inv = ldexpf(1.f, -kw);
+    out.tc = pk.halfs.size();
+    pk.halfs.resize(out.tc + (size_t)G * 9 * 256, 0);
+    for (int g = 0; g < G; g++)
+        for (int tap = 0; tap < 9; tap++)
+            for (int n = 0; n < 16; n++)
+                for (int k = 0; k < 16; k++) {
+                    const int co = n & 7, ci = g * 8 + (k & 7);
+                    const float wv = ci < cin ? w[(co * cin + ci) * 9 + tap] * scale : 0.f;
+                    const __half hi = __float2half_rn(wv);
+                    const __half lo = __float2half_rn((wv - __half2float(hi)) * 2048.f);
+                    __half val = __float2half_rn(0.f);
+                    if (n < 8) { if (k < 8) val = hi; }
+                    else val = (k < 8) ? lo : hi;
+                    const int byte = (n / 8) * 256 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2;
+                    uint16_t bits;
+                    memcpy(&bits, &val, 2);
+                    pk.halfs[out.tc + (size_t)(g * 9 + tap) * 256 + byte / 2] = bits;
+                }
+}
+#endif
+
 struct Cursor {
     const float* p;
     size_t left;
@@ -282,6 +328,10 @@ static void pack_double_conv(Packer& pk, Cursor& cur, ConvW out[2], int cin, int
     out[1].w = pack_conv3(pk, w1, cout, cmid);
     out[1].b = pack_vec(pk, b1, cout);
     out[1].slope = out[0].slope;
+#ifdef HN_HAVE_TC
+    if (cmid == 8) pack_tc(pk, w0, cin, out[0]);
+    if (cout == 8 && cmid == 8) pack_tc(pk, w1, cmid, out[1]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -295,6 +345,27 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
     if (!attr_done[c->device & 15]) {
         HN_CUDA(cudaFuncSetAttribute(conv3x3_kernel<SRC, COUT, PRELU, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[c->device & 15] = true;
+    }
+#endif
+#ifdef HN_HAVE_TC
+    if constexpr (COUT == 8) {
+        if (c->engine == 1 && a.tc_bmat != nullptr && a.H >= c->tc_min_res) {
+            static bool tc_attr_done[16] = {false};
+            if (!tc_attr_done[c->device & 15]) {
+                HN_CUDA(cudaFuncSetAttribute(tc::conv3x3_tc_kernel<SRC, PRELU, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)tc::smem_bytes(SRC)));
+                tc_attr_done[c->device & 15] = true;
+            }
+            tc::Args t;
+            t.inA = a.inA; t.inB = a.inB; t.sigma = a.sigma;
+            t.bmat = reinterpret_cast<const __half*>(a.tc_bmat);
+            t.bias = a.bias; t.slope = a.slope; t.out = a.out; t.wo = a.wo; t.bo = a.bo; t.wf = a.wf; t.dwf_out = a.dwf_out;
+            t.error_flag = c->err_flag; t.w_inv_scale = a.tc_inv; t.H = a.H; t.W = a.W;
+            dim3 tgrid((a.W + tc::TX - 1) / tc::TX, (a.H + tc::TY - 1) / tc::TY, B);
+            tc::conv3x3_tc_kernel<SRC, PRELU, EPI><<<tgrid, dim3(tc::THREADS), tc::smem_bytes(SRC), st>>>(t);
+            c->launches++;
+            return HN_OK;
+        }
     }
 #endif
     dim3 grid((a.W + C3_TX - 1) / C3_TX, (a.H + C3_TY - 1) / C3_TY, B);
@@ -315,6 +386,8 @@ static Conv3Args conv_args(hn_ctx* c, const ConvW& w, const float* inA, const fl
     a.out = out;
     a.H = r;
     a.W = r;
+    a.tc_bmat = (w.tc != (size_t)-1 && c->tcw) ? (const void*)(c->tcw + w.tc) : nullptr;
+    a.tc_inv = w.tc_inv;
     return a;
 }
 
@@ -521,7 +594,15 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     A_(c->ssq1, B);
     A_(c->iter_dev, 4);
     A_(c->wdev, 65536);
+    A_(c->tcw, 81920);
+    A_(c->err_flag, 4);
 #undef A_
+    if (cudaMemset(c->err_flag, 0, 16) != cudaSuccess) return cleanup(fail(HN_ERR_CUDA, "cudaMemset failed"));
+    if (const char* mr = getenv("HELMNET_TC_MIN_RES")) c->tc_min_res = atoi(mr);
+    if (const char* en = getenv("HELMNET_ENGINE")) c->engine = atoi(en) == 1 ? 1 : 0;
+#ifdef HN_EMU
+    c->engine = 0;
+#endif
     if (cudaMemset(c->iter_dev, 0, 16) != cudaSuccess) return cleanup(fail(HN_ERR_CUDA, "cudaMemset failed"));
     for (int d = 0; d < kDepth; d++)
         for (int k = 0; k < 2; k++)
@@ -590,6 +671,8 @@ int hn_load_weights(hn_ctx* c, const float* host_blob, size_t n_floats) {
     HN_CUDA(cudaDeviceSynchronize());
 #endif
     HN_CUDA(cudaMemcpy(c->wdev, pk.blob.data(), pk.blob.size() * 4, cudaMemcpyHostToDevice));
+    if (pk.halfs.size() > 81920) return fail(HN_ERR_STATE, "tensor-core weight images exceed the reserved buffer");
+    if (!pk.halfs.empty()) HN_CUDA(cudaMemcpy(c->tcw, pk.halfs.data(), pk.halfs.size() * 2, cudaMemcpyHostToDevice));
     c->weights_set = true;
     return HN_OK;
 }
@@ -892,9 +975,24 @@ int hn_debug_tensor(hn_ctx* c, const char* name, float* d_out, int batch, void* 
 
 int hn_set_engine(hn_ctx* c, int engine) {
     if (!c) return fail(HN_ERR_ARG, "ctx is NULL");
-    if (engine != 0) return fail(HN_ERR_ARG, "only engine 0 (fp32 CUDA-core) is available in this build");
+#ifdef HN_HAVE_TC
+    if (engine != 0 && engine != 1) return fail(HN_ERR_ARG, "engine must be 0 (fp32 CUDA cores) or 1 (tcgen05 split-fp16)");
+#else
+    if (engine != 0) return fail(HN_ERR_ARG, "only engine 0 is available in the emulator build");
+#endif
     c->engine = engine;
     return c->engine;
+}
+
+int hn_sync_check(hn_ctx* c, void* stream) {
+    if (!c) return fail(HN_ERR_ARG, "ctx is NULL");
+#ifndef HN_EMU
+    HN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    int flag = 0;
+    HN_CUDA(cudaMemcpy(&flag, c->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag != 0) return fail(HN_ERR_CUDA, "tcgen05 watchdog: an MMA completion barrier was never signalled");
+#endif
+    return HN_OK;
 }
 
 int hn_profile_iteration(hn_ctx* c, float out_ms[2], void* stream) {

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import inspect
+import os
 import weakref
 from typing import List, Optional
 
@@ -180,6 +181,7 @@ class IterativeSolver(nn.Module):
         self._ctx_max_batch = 0
         self._weights_dirty = True
         self._source_dirty = True
+        self._engine = int(os.environ.get("HELMNET_ENGINE", "0"))
         self.register_buffer("sigmas", None)
         self.set_laplacian()
         self.setup_source()
@@ -353,6 +355,8 @@ class IterativeSolver(nn.Module):
                                     float(hp.k), float(hp.omega)), "hn_create")
             self._ctx, self._ctx_key, self._ctx_max_batch = ctx, key, max_batch
             self._weights_dirty = self._source_dirty = True
+            if lib.requires_cuda:
+                lib.check(lib.hn_set_engine(ctx, self._engine), "hn_set_engine")
         if self._weights_dirty:
             blob = self.f.weight_blob()
             lib.check(lib.hn_load_weights(self._ctx, self._ptr(blob), blob.numel()), "hn_load_weights")
@@ -372,6 +376,17 @@ class IterativeSolver(nn.Module):
             self._source_keepalive = src
             self._source_dirty = False
         return self._ctx
+
+    def set_engine(self, engine: int):
+        """0: fp32 CUDA-core convolutions; 1: tcgen05 split-fp16 tensor-core convolutions (C_out = 8 layers)."""
+        self._engine = int(engine)
+        if self._ctx is not None:
+            self.lib.check(self.lib.hn_set_engine(self._ctx, self._engine), "hn_set_engine")
+
+    def sync_check(self):
+        """Synchronise and raise if a kernel recorded a device-side fault."""
+        if self._ctx is not None:
+            self.lib.check(self.lib.hn_sync_check(self._ctx, self._stream()), "hn_sync_check")
 
     def sync_weights(self):
         """Call after mutating ``solver.f`` parameters in place."""

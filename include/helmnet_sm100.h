@@ -121,6 +121,9 @@ int hn_debug_tensor(hn_ctx* ctx, const char* name, float* d_out, int batch, void
 /* Selects the convolution engine: 0 = fp32 CUDA-core kernels, 1 = tcgen05 split-TF32 kernels for the
  * layers that have one.  Returns the engine now in effect or a negative status. */
 int hn_set_engine(hn_ctx* ctx, int engine);
+/* Synchronises `stream` and reports device-side faults recorded by the kernels (tcgen05 completion
+ * watchdog). Returns HN_OK or HN_ERR_CUDA. */
+int hn_sync_check(hn_ctx* ctx, void* stream);
 /* Per-stage device time of the last hn_profile_iteration() in milliseconds:
  * out[0] = UNet stage, out[1] = spectral residual stage. Synchronous; runs ONE iteration. */
 int hn_profile_iteration(hn_ctx* ctx, float out_ms[2], void* stream);

@@ -38,13 +38,21 @@ def f_weights():
 
 
 @pytest.fixture(scope="session")
-def cuda_solver():
-    """IterativeSolver on cuda:0 through the product library (fails loudly if it is missing)."""
+def _cuda_solver_base():
     from helmnet_b200 import IterativeSolver
     s = IterativeSolver.load_from_checkpoint(CKPT, strict=False, test_data_path=None)
     s.freeze()
     s.to("cuda:0")
     return s
+
+
+@pytest.fixture(params=[0, 1], ids=["simt", "tcgen05"])
+def cuda_solver(request, _cuda_solver_base):
+    """IterativeSolver on cuda:0 through the product library (fails loudly if it is missing), once per
+    convolution engine: fp32 CUDA cores and tcgen05 split-fp16."""
+    _cuda_solver_base.set_engine(request.param)
+    yield _cuda_solver_base
+    _cuda_solver_base.sync_check()
 
 
 @pytest.fixture(scope="session")
