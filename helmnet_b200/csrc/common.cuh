@@ -69,4 +69,21 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// Running max |x| of a tensor, kept as the bit pattern of a non-negative float (unsigned order == float order).
+// Producers publish it so that the tcgen05 convolutions can pick a power-of-two block scale for their fp16
+// operand split without a second pass over the data.  Call with the whole warp; lane 0 publishes.
+__device__ __forceinline__ void publish_amax(unsigned* slot, float local_max) {
+    if (slot == nullptr) return;
+    const float m = warp_max(local_max);
+    if ((threadIdx.x & 31) == 0) {
+        const unsigned bits = __float_as_uint(m);
+        if (bits > *reinterpret_cast<volatile unsigned*>(slot)) atomicMax(slot, bits);
+    }
+}
+
 }  // namespace hn

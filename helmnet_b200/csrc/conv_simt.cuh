@@ -48,6 +48,9 @@ struct Conv3Args {
     const float* bo;      // EPI_OUTC: outc bias [2]
     float* wf;            // EPI_OUTC: wavefield float2 [B][H][W], updated in place
     float* dwf_out;       // EPI_OUTC: when non-null store the raw network output here instead
+    unsigned* amax_out;         // running max |out| slot (see publish_amax), or null
+    const unsigned* amax_in0;   // tcgen05 engine only: max |x| slots of the two sources
+    const unsigned* amax_in1;
     const void* tc_bmat;  // tcgen05 engine only: fp16 split-weight image of this layer (unused by the SIMT kernel)
     float tc_inv;         // tcgen05 engine only: 2^-kw
     int H, W;
@@ -181,14 +184,15 @@ __global__ void __launch_bounds__(C3_THREADS) conv3x3_kernel(Conv3Args a) {
 
     // ---- epilogue ----------------------------------------------------------------------------------
     const int gx = tx0 + tx;
-    if (gx >= W) return;
+    const bool colok = gx < W;
     float slope = 0.f;
     if (PRELU) slope = __ldg(a.slope);
     if constexpr (EPI == EPI_STORE) {
+        float lmax = 0.f;
 #pragma unroll
         for (int r = 0; r < C3_RP; r++) {
             const int gy = ty0 + wy + r;
-            if (gy >= H) break;
+            if (!colok || gy >= H) continue;
             float o[COUT];
 #pragma unroll
             for (int c = 0; c < CP; c++) {
@@ -199,6 +203,8 @@ __global__ void __launch_bounds__(C3_THREADS) conv3x3_kernel(Conv3Args a) {
 #pragma unroll
                 for (int c = 0; c < COUT; c++) o[c] = o[c] >= 0.f ? o[c] : slope * o[c];  // signed slope
             }
+#pragma unroll
+            for (int c = 0; c < COUT; c++) lmax = fmaxf(lmax, fabsf(o[c]));
             float* dst = a.out + (img + (size_t)gy * W + gx) * COUT;
             if constexpr (COUT == 8) {
                 reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -207,6 +213,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3x3_kernel(Conv3Args a) {
                 reinterpret_cast<float2*>(dst)[0] = make_float2(o[0], o[1]);
             }
         }
+        publish_amax(a.amax_out, lmax);
     } else {  // EPI_OUTC (COUT == 8)
         float wo0[8], wo1[8];
 #pragma unroll
@@ -218,7 +225,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3x3_kernel(Conv3Args a) {
 #pragma unroll
         for (int r = 0; r < C3_RP; r++) {
             const int gy = ty0 + wy + r;
-            if (gy >= H) break;
+            if (!colok || gy >= H) continue;
             float o0 = bo0, o1 = bo1;
 #pragma unroll
             for (int c = 0; c < CP; c++) {
@@ -249,6 +256,7 @@ struct DownArgs {
     const float* w;     // packed [2 planes][8 ky][8 kx][4 ci][8 co]
     const float* bias;  // [8]
     float* out;         // NHWC8 [B][H/2][W/2]
+    unsigned* amax_out; // running max |out| slot or null
     int H, W;           // input resolution
 };
 constexpr int DN_TX = 32, DN_RP = 4, DN_WARPS = 4, DN_TY = DN_RP * DN_WARPS;  // output tile 32 x 16
@@ -322,15 +330,18 @@ __global__ void __launch_bounds__(DN_THREADS) down_kernel(DownArgs a) {
         }
     }
     const int ox = ox0 + tx;
-    if (ox >= Wo) return;
+    float lmax = 0.f;
 #pragma unroll
     for (int r = 0; r < DN_RP; r++) {
         const int oy = oy0 + wy + r;
-        if (oy >= Ho) break;
+        if (ox >= Wo || oy >= Ho) continue;
         float4* dst = reinterpret_cast<float4*>(a.out + (((size_t)b * Ho + oy) * Wo + ox) * 8);
         dst[0] = make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y);
         dst[1] = make_float4(acc[r][2].x, acc[r][2].y, acc[r][3].x, acc[r][3].y);
+#pragma unroll
+        for (int c = 0; c < 4; c++) lmax = fmaxf(lmax, fmaxf(fabsf(acc[r][c].x), fabsf(acc[r][c].y)));
     }
+    publish_amax(a.amax_out, lmax);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -344,6 +355,7 @@ struct UpArgs {
     const float* w;     // packed [4 classes][2 planes][4 ty][4 tx][4 ci][8 co]
     const float* bias;  // [8]
     float* out;         // NHWC8 [B][2Hi][2Wi]
+    unsigned* amax_out; // running max |out| slot or null
     int Hi, Wi;
 };
 constexpr int UP_TL = 16;                 // low-res cells per tile side -> 32 x 32 outputs
@@ -418,15 +430,18 @@ __global__ void __launch_bounds__(UP_THREADS) up_kernel(UpArgs a) {
         }
     }
     const int ox = 2 * (cx0 + cx) + pxp;
-    if (ox >= Wo) return;
+    float lmax = 0.f;
 #pragma unroll
     for (int r = 0; r < UP_RP; r++) {
         const int oy = 2 * (cy0 + cyb + r) + py;
-        if (oy >= Ho) break;
+        if (ox >= Wo || oy >= Ho) continue;
         float4* dst = reinterpret_cast<float4*>(a.out + (((size_t)b * Ho + oy) * Wo + ox) * 8);
         dst[0] = make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y);
         dst[1] = make_float4(acc[r][2].x, acc[r][2].y, acc[r][3].x, acc[r][3].y);
+#pragma unroll
+        for (int c = 0; c < 4; c++) lmax = fmaxf(lmax, fmaxf(fabsf(acc[r][c].x), fabsf(acc[r][c].y)));
     }
+    publish_amax(a.amax_out, lmax);
 }
 
 }  // namespace hn

@@ -88,6 +88,7 @@ struct hn_ctx {
     float* wdev = nullptr;
     uint16_t* tcw = nullptr;   // fp16 split-weight images for the tcgen05 convolutions
     int* err_flag = nullptr;   // device watchdog flag of the tcgen05 kernels
+    unsigned* amax = nullptr;  // [64] running max |x| per activation tensor (publish_amax), feeds the fp16 block scales
     int tc_min_res = 16;       // use the tensor-core kernels for levels with resolution >= this
     Weights W;
     // residual norms
@@ -104,6 +105,9 @@ struct hn_ctx {
 #endif
     std::vector<void*> allocs;
 };
+
+// amax slot ids
+enum : int { S_X = 0, S_MID = 5, S_SKIP = 10, S_UPO = 14, S_DEC = 18, S_BOT = 22, S_STATE = 23 /* + 2*d + buf */, S_IN6 = 31, S_DMID = 32, S_IMID = 36, S_COUNT = 37 };
 
 static int dalloc(hn_ctx* c, void** p, size_t bytes) {
     if (bytes == 0) bytes = 16;
@@ -349,7 +353,7 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
 #endif
 #ifdef HN_HAVE_TC
     if constexpr (COUT == 8) {
-        if (c->engine == 1 && a.tc_bmat != nullptr && a.H >= c->tc_min_res) {
+        if (c->engine == 1 && a.tc_bmat != nullptr && a.H >= c->tc_min_res && (SRC == SRC_INC || a.amax_in0 != nullptr)) {
             static bool tc_attr_done[16] = {false};
             if (!tc_attr_done[c->device & 15]) {
                 HN_CUDA(cudaFuncSetAttribute(tc::conv3x3_tc_kernel<SRC, PRELU, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -360,6 +364,7 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
             t.inA = a.inA; t.inB = a.inB; t.sigma = a.sigma;
             t.bmat = reinterpret_cast<const __half*>(a.tc_bmat);
             t.bias = a.bias; t.slope = a.slope; t.out = a.out; t.wo = a.wo; t.bo = a.bo; t.wf = a.wf; t.dwf_out = a.dwf_out;
+            t.amax_in0 = a.amax_in0; t.amax_in1 = a.amax_in1; t.amax_out = a.amax_out;
             t.error_flag = c->err_flag; t.w_inv_scale = a.tc_inv; t.H = a.H; t.W = a.W;
             dim3 tgrid((a.W + tc::TX - 1) / tc::TX, (a.H + tc::TY - 1) / tc::TY, B);
             tc::conv3x3_tc_kernel<SRC, PRELU, EPI><<<tgrid, dim3(tc::THREADS), tc::smem_bytes(SRC), st>>>(t);
@@ -374,9 +379,13 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
     return HN_OK;
 }
 
-static Conv3Args conv_args(hn_ctx* c, const ConvW& w, const float* inA, const float* inB, float* out, int r) {
+static Conv3Args conv_args(hn_ctx* c, const ConvW& w, const float* inA, const float* inB, float* out, int r, int slot_out = -1,
+                           int slot_in0 = -1, int slot_in1 = -1) {
     Conv3Args a;
     memset(&a, 0, sizeof(a));
+    a.amax_out = slot_out >= 0 ? c->amax + slot_out : nullptr;
+    a.amax_in0 = slot_in0 >= 0 ? c->amax + slot_in0 : nullptr;
+    a.amax_in1 = slot_in1 >= 0 ? c->amax + slot_in1 : (slot_in0 >= 0 ? c->amax + slot_in0 : nullptr);
     a.inA = inA;
     a.inB = inB;
     a.sigma = c->sigma1d;
@@ -408,30 +417,40 @@ static int set_smem_attrs(hn_ctx* c) {
 static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool raw_out) {
     const Weights& W = c->W;
     const int cur = c->cur, nxt = cur ^ 1;
+    // zero the amax slots of everything this pass (re)produces; keep the current hidden-state slots and in6
+    {
+        unsigned long long mask = 0;
+        for (int i = 0; i < S_COUNT; i++) mask |= 1ull << i;
+        for (int d = 0; d < kDepth; d++) mask &= ~(1ull << (S_STATE + 2 * d + cur));
+        mask &= ~(1ull << S_IN6);
+        HN_LAUNCH(reset_amax_kernel, dim3(1), dim3(64), 0, st, c->amax, mask);
+        c->launches++;
+    }
     // inc
     {
-        Conv3Args a = conv_args(c, W.inc[0], from_in6 ? c->in6 : c->wf, c->res, c->mid[0], c->r[0]);
+        Conv3Args a = conv_args(c, W.inc[0], from_in6 ? c->in6 : c->wf, c->res, c->mid[0], c->r[0], S_IMID, from_in6 ? S_IN6 : -1);
         if (from_in6) HN_TRY((launch_conv3<SRC_A8, 8, true, EPI_STORE>(c, a, B, st)));
         else HN_TRY((launch_conv3<SRC_INC, 8, true, EPI_STORE>(c, a, B, st)));
-        Conv3Args a2 = conv_args(c, W.inc[1], c->mid[0], nullptr, c->x[0], c->r[0]);
+        Conv3Args a2 = conv_args(c, W.inc[1], c->mid[0], nullptr, c->x[0], c->r[0], S_X + 0, S_IMID);
         HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, a2, B, st)));
     }
     // encoder
     for (int d = 0; d < kDepth; d++) {
         const int r = c->r[d];
-        Conv3Args s0 = conv_args(c, W.sig[d][0], c->x[d], c->state[d][cur], c->mid[d], r);
+        Conv3Args s0 = conv_args(c, W.sig[d][0], c->x[d], c->state[d][cur], c->mid[d], r, S_MID + d, S_X + d, S_STATE + 2 * d + cur);
         HN_TRY((launch_conv3<SRC_A8_B2, 8, true, EPI_STORE>(c, s0, B, st)));
-        Conv3Args s1 = conv_args(c, W.sig[d][1], c->mid[d], nullptr, c->skip[d], r);
+        Conv3Args s1 = conv_args(c, W.sig[d][1], c->mid[d], nullptr, c->skip[d], r, S_SKIP + d, S_MID + d);
         HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, s1, B, st)));
         Conv3Args t0 = conv_args(c, W.sta[d][0], c->skip[d], c->state[d][cur], c->mid2[d], r);
         HN_TRY((launch_conv3<SRC_A8_B2, 2, true, EPI_STORE>(c, t0, B, st)));
-        Conv3Args t1 = conv_args(c, W.sta[d][1], c->mid2[d], nullptr, c->state[d][nxt], r);
+        Conv3Args t1 = conv_args(c, W.sta[d][1], c->mid2[d], nullptr, c->state[d][nxt], r, S_STATE + 2 * d + nxt);
         HN_TRY((launch_conv3<SRC_A2, 2, false, EPI_STORE>(c, t1, B, st)));
         DownArgs dn;
         dn.in = c->skip[d];
         dn.w = c->wdev + W.down[d].w;
         dn.bias = c->wdev + W.down[d].b;
         dn.out = c->x[d + 1];
+        dn.amax_out = c->amax + S_X + d + 1;
         dn.H = r;
         dn.W = r;
         dim3 g((r / 2 + DN_TX - 1) / DN_TX, (r / 2 + DN_TY - 1) / DN_TY, B);
@@ -441,9 +460,9 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
     // bottom
     {
         const int r = c->r[kDepth];
-        Conv3Args b0 = conv_args(c, W.bot[0], c->x[kDepth], nullptr, c->mid[kDepth], r);
+        Conv3Args b0 = conv_args(c, W.bot[0], c->x[kDepth], nullptr, c->mid[kDepth], r, S_MID + kDepth, S_X + kDepth);
         HN_TRY((launch_conv3<SRC_A8, 8, true, EPI_STORE>(c, b0, B, st)));
-        Conv3Args b1 = conv_args(c, W.bot[1], c->mid[kDepth], nullptr, c->bot, r);
+        Conv3Args b1 = conv_args(c, W.bot[1], c->mid[kDepth], nullptr, c->bot, r, S_BOT, S_MID + kDepth);
         HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, b1, B, st)));
     }
     // decoder
@@ -454,14 +473,16 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
         up.w = c->wdev + W.up[d].w;
         up.bias = c->wdev + W.up[d].b;
         up.out = c->upo[d];
+        up.amax_out = c->amax + S_UPO + d;
         up.Hi = r / 2;
         up.Wi = r / 2;
         dim3 g((r / 2 + UP_TL - 1) / UP_TL, (r / 2 + UP_TL - 1) / UP_TL, B);
         HN_LAUNCH(up_kernel, g, dim3(UP_THREADS), UP_SMEM, st, up);
         c->launches++;
-        Conv3Args d0 = conv_args(c, W.dec[d][0], c->upo[d], c->skip[d], c->mid[d], r);
+        // mid[d] is reused as scratch by inc / encoder / decoder; each use has its own amax slot
+        Conv3Args d0 = conv_args(c, W.dec[d][0], c->upo[d], c->skip[d], c->mid[d], r, S_DMID + d, S_UPO + d, S_SKIP + d);
         HN_TRY((launch_conv3<SRC_A8_B8, 8, true, EPI_STORE>(c, d0, B, st)));
-        Conv3Args d1 = conv_args(c, W.dec[d][1], c->mid[d], nullptr, c->dec[d], r);
+        Conv3Args d1 = conv_args(c, W.dec[d][1], c->mid[d], nullptr, c->dec[d], r, S_DEC + d, S_DMID + d);
         if (d > 0) {
             HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, d1, B, st)));
         } else {
@@ -596,7 +617,9 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     A_(c->wdev, 65536);
     A_(c->tcw, 81920);
     A_(c->err_flag, 4);
+    A_(c->amax, 64);
 #undef A_
+    if (cudaMemset(c->amax, 0, 256) != cudaSuccess) return cleanup(fail(HN_ERR_CUDA, "cudaMemset failed"));
     if (cudaMemset(c->err_flag, 0, 16) != cudaSuccess) return cleanup(fail(HN_ERR_CUDA, "cudaMemset failed"));
     if (const char* mr = getenv("HELMNET_TC_MIN_RES")) c->tc_min_res = atoi(mr);
     if (const char* en = getenv("HELMNET_ENGINE")) c->engine = atoi(en) == 1 ? 1 : 0;
@@ -710,8 +733,10 @@ int hn_reset(hn_ctx* c, const float* d_sos, int batch, void* stream) {
               reinterpret_cast<float2*>(c->res), reinterpret_cast<const float2*>(c->src), c->src_batch, (float)c->omega, hw,
               total);
     c->launches++;
-    for (int d = 0; d < kDepth; d++)
+    for (int d = 0; d < kDepth; d++) {
         HN_CUDA(cudaMemsetAsync(c->state[d][c->cur], 0, (size_t)batch * c->r[d] * c->r[d] * 8, st));
+        HN_CUDA(cudaMemsetAsync(c->amax + S_STATE + 2 * d + c->cur, 0, sizeof(unsigned), st));
+    }
     HN_CUDA(cudaGetLastError());
     c->batch = batch;
     c->problem_set = true;
@@ -740,8 +765,10 @@ int hn_set_state(hn_ctx* c, const float* d_wf, const float* d_res, const float* 
         for (int d = 0; d < kDepth; d++) {
             const int p = c->r[d] * c->r[d];
             const size_t tot = (size_t)batch * p;
+            HN_CUDA(cudaMemsetAsync(c->amax + S_STATE + 2 * d + c->cur, 0, sizeof(unsigned), st));
             HN_LAUNCH(nchw2_strided_to_c2_kernel, dim3(grid1d(tot)), dim3(LAY_THREADS), 0, st, d_hflat + off,
-                      reinterpret_cast<float2*>(c->state[d][c->cur]), p, tot, (size_t)2 * c->state_len, (size_t)c->state_len);
+                      reinterpret_cast<float2*>(c->state[d][c->cur]), p, tot, (size_t)2 * c->state_len, (size_t)c->state_len,
+                      c->amax + S_STATE + 2 * d + c->cur);
             c->launches++;
             off += p;
         }
@@ -937,7 +964,8 @@ int hn_unet(hn_ctx* c, const float* d_in, float* d_out, int batch, void* stream)
     cudaStream_t st = (cudaStream_t)stream;
     const int hw = c->n * c->n;
     const size_t total = (size_t)batch * hw;
-    HN_LAUNCH(nchw6_to_nhwc8_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_in, c->in6, hw, total);
+    HN_CUDA(cudaMemsetAsync(c->amax + S_IN6, 0, sizeof(unsigned), st));
+    HN_LAUNCH(nchw6_to_nhwc8_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_in, c->in6, hw, total, c->amax + S_IN6);
     c->launches++;
     HN_TRY(launch_unet(c, batch, st, true, true));
     c->cur ^= 1;

@@ -29,11 +29,15 @@ __global__ void c2_to_nchw2_kernel(const float2* __restrict__ in, float* __restr
 }
 // gather variant of the above: [B,2,*] with batch/channel strides -> float2 [B,hw]
 __global__ void nchw2_strided_to_c2_kernel(const float* __restrict__ in, float2* __restrict__ out, int hw, size_t total,
-                                           size_t in_bstride, size_t in_cstride) {
+                                           size_t in_bstride, size_t in_cstride, unsigned* amax_out) {
+    float lmax = 0.f;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t b = i / hw, p = i - b * hw;
-        out[i] = make_float2(in[b * in_bstride + p], in[b * in_bstride + in_cstride + p]);
+        const float2 v = make_float2(in[b * in_bstride + p], in[b * in_bstride + in_cstride + p]);
+        out[i] = v;
+        lmax = fmaxf(lmax, fmaxf(fabsf(v.x), fabsf(v.y)));
     }
+    publish_amax(amax_out, lmax);
 }
 // arbitrary 4-D strides (source maps arrive as permuted views, hybridnet.py:152,167)
 __global__ void src_strided_to_c2_kernel(const float* __restrict__ in, float2* __restrict__ out, int n, size_t total,
@@ -59,17 +63,23 @@ __global__ void reset_kernel(const float* __restrict__ sos, float* __restrict__ 
     }
 }
 // [B,6,H,W] -> NHWC8 (channels 6,7 zero): input of HybridNet.forward when called directly
-__global__ void nchw6_to_nhwc8_kernel(const float* __restrict__ in, float* __restrict__ out, int hw, size_t total) {
+__global__ void nchw6_to_nhwc8_kernel(const float* __restrict__ in, float* __restrict__ out, int hw, size_t total,
+                                      unsigned* amax_out) {
+    float lmax = 0.f;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t b = i / hw, p = i - b * hw;
         float v[8];
 #pragma unroll
-        for (int c = 0; c < 6; c++) v[c] = in[(b * 6 + c) * hw + p];
+        for (int c = 0; c < 6; c++) {
+            v[c] = in[(b * 6 + c) * hw + p];
+            lmax = fmaxf(lmax, fabsf(v[c]));
+        }
         v[6] = v[7] = 0.f;
         float4* o = reinterpret_cast<float4*>(out + i * 8);
         o[0] = make_float4(v[0], v[1], v[2], v[3]);
         o[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
+    publish_amax(amax_out, lmax);
 }
 // NHWC8 -> [B,8,H,W] (debug taps)
 __global__ void nhwc8_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int hw, size_t total) {
@@ -82,6 +92,11 @@ __global__ void nhwc8_to_nchw_kernel(const float* __restrict__ in, float* __rest
 __global__ void finalize_rmse_kernel(const double* __restrict__ ssq, float* __restrict__ rmse, int count, double inv_count) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
         rmse[i] = (float)sqrt(ssq[i] * inv_count);
+}
+// zero the amax slots whose bit is set in `mask` (slots of tensors that are re-produced in this UNet pass)
+__global__ void reset_amax_kernel(unsigned* slots, unsigned long long mask) {
+    const int i = threadIdx.x;
+    if (i < 64 && ((mask >> i) & 1ull)) slots[i] = 0u;
 }
 __global__ void advance_iter_kernel(int* it) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *it += 1;

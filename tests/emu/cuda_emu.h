@@ -84,6 +84,9 @@ static inline void __syncthreads() { hn_emu::yield_wait(1); }
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
 static inline double atomicAdd(double* p, double v) { double o = *p; *p = o + v; return o; }
+static inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
 static inline float __shfl_xor_sync(unsigned, float v, int lanemask) {
     uint32_t u;
