@@ -159,7 +159,10 @@ def test_full_size_properties(cuda_solver):
     assert torch.equal(again["wavefields"][0], a_wf)
     assert rel_l2(again["residual_rmse"], a_rm) < 1e-6
     one = s.forward(sos[5:6], num_iterations=8)
-    assert torch.equal(one["wavefields"][0][0], a_wf[5])
+    if s._engine == 0:
+        assert torch.equal(one["wavefields"][0][0], a_wf[5])
+    else:   # the fp16 block scale is per tensor (whole batch), so batch composition moves the last bits
+        assert rel_l2(one["wavefields"][0][0], a_wf[5]) < 5e-6
     assert torch.equal(a_wf[1], a_wf[5])                 # identical inputs at different batch slots
 
 
