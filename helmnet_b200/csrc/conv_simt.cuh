@@ -51,6 +51,7 @@ struct Conv3Args {
     unsigned* amax_out;         // running max |out| slot (see publish_amax), or null
     const unsigned* amax_in0;   // tcgen05 engine only: max |x| slots of the two sources
     const unsigned* amax_in1;
+    const void* tcr_bmat; // row-streaming tcgen05 kernel: fp16 split-weight image (N = 48)
     const void* tc_bmat;  // tcgen05 engine only: fp16 split-weight image of this layer (unused by the SIMT kernel)
     float tc_inv;         // tcgen05 engine only: 2^-kw
     int H, W;
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3x3_kernel(Conv3Args a) {
             wo1[c] = __ldg(a.wo + 8 + c);
         }
         const float bo0 = __ldg(a.bo), bo1 = __ldg(a.bo + 1);
+        float lmax = 0.f;
 #pragma unroll
         for (int r = 0; r < C3_RP; r++) {
             const int gy = ty0 + wy + r;
@@ -240,9 +242,12 @@ __global__ void __launch_bounds__(C3_THREADS) conv3x3_kernel(Conv3Args a) {
             } else {
                 float2* wfp = reinterpret_cast<float2*>(a.wf) + p;
                 const float2 u = *wfp;
-                *wfp = make_float2(o0 / 1e3f + u.x, o1 / 1e3f + u.y);  // hybridnet.py:570  d_wavefield / 1e3 + wavefield
+                const float2 nw = make_float2(o0 / 1e3f + u.x, o1 / 1e3f + u.y);  // hybridnet.py:570  d_wavefield / 1e3 + wavefield
+                *wfp = nw;
+                lmax = fmaxf(lmax, fmaxf(fabsf(nw.x), fabsf(nw.y)));
             }
         }
+        publish_amax(a.amax_out, lmax);
     }
 }
 

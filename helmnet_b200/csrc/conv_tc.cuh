@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(THREADS, (groups_of(SRC) == 1) ? 4 : 2) conv3x
                 const float s = fmaf(__uint_as_float(v[8 + c]), 1.f / 2048.f, __uint_as_float(v[c]));
                 o[c] = fmaf(s, out_scale, bias[c]);
                 if (PRELU) o[c] = o[c] >= 0.f ? o[c] : slope * o[c];
-                lmax = fmaxf(lmax, fabsf(o[c]));
+                if (EPI == EPI_STORE) lmax = fmaxf(lmax, fabsf(o[c]));
             }
             const size_t pix = img + (size_t)gy * W + gx;
             if (EPI == EPI_STORE) {
@@ -307,12 +307,14 @@ __global__ void __launch_bounds__(THREADS, (groups_of(SRC) == 1) ? 4 : 2) conv3x
                 } else {
                     float2* wfp = reinterpret_cast<float2*>(a.wf) + pix;
                     const float2 u = *wfp;
-                    *wfp = make_float2(o0 / 1e3f + u.x, o1 / 1e3f + u.y);   // hybridnet.py:570
+                    const float2 nw = make_float2(o0 / 1e3f + u.x, o1 / 1e3f + u.y);   // hybridnet.py:570
+                    *wfp = nw;
+                    lmax = fmaxf(lmax, fmaxf(fabsf(nw.x), fabsf(nw.y)));
                 }
             }
         }
     }
-    if (EPI == EPI_STORE) publish_amax(a.amax_out, lmax);
+    publish_amax(a.amax_out, lmax);
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));

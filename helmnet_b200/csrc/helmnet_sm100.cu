@@ -23,6 +23,7 @@
 #include "spectral.cuh"
 #ifndef HN_EMU
 #include "conv_tc.cuh"
+#include "conv_tcr.cuh"
 #define HN_HAVE_TC 1
 #endif
 
@@ -50,6 +51,7 @@ static int fail(int code, const std::string& msg) {
 struct ConvW {      // offsets (in floats) into the packed device blob
     size_t w = 0, b = 0, slope = 0;
     size_t tc = (size_t)-1;   // offset (in halfs) of the tcgen05 B-operand image, C_out = 8 layers only
+    size_t tcr = (size_t)-1;  // same for the row-streaming kernel (N = 48 images)
     float tc_inv = 1.f;       // 2^-kw, inverse of the layer's weight block scale
 };
 struct Weights {
@@ -90,6 +92,7 @@ struct hn_ctx {
     int* err_flag = nullptr;   // device watchdog flag of the tcgen05 kernels
     unsigned* amax = nullptr;  // [64] running max |x| per activation tensor (publish_amax), feeds the fp16 block scales
     int tc_min_res = 16;       // use the tensor-core kernels for levels with resolution >= this
+    int tcr_min_res = 48;      // row-streaming tensor-core kernel for widths >= this (128-wide strips)
     Weights W;
     // residual norms
     double* ssq = nullptr;
@@ -107,7 +110,7 @@ struct hn_ctx {
 };
 
 // amax slot ids
-enum : int { S_X = 0, S_MID = 5, S_SKIP = 10, S_UPO = 14, S_DEC = 18, S_BOT = 22, S_STATE = 23 /* + 2*d + buf */, S_IN6 = 31, S_DMID = 32, S_IMID = 36, S_COUNT = 37 };
+enum : int { S_X = 0, S_MID = 5, S_SKIP = 10, S_UPO = 14, S_DEC = 18, S_BOT = 22, S_STATE = 23 /* + 2*d + buf */, S_IN6 = 31, S_DMID = 32, S_IMID = 36, S_WF = 37 /* +buf */, S_RES = 39 /* +buf */, S_COUNT = 41 };
 
 static int dalloc(hn_ctx* c, void** p, size_t bytes) {
     if (bytes == 0) bytes = 16;
@@ -305,6 +308,36 @@ static void pack_tc(Packer& pk, const float* w, int cin, ConvW& out) {
                     pk.halfs[out.tc + (size_t)(g * 9 + tap) * 256 + byte / 2] = bits;
                 }
 }
+// Row-streaming kernel (conv_tcr.cuh): per (group g, dx) a 48 x 16 fp16 B operand, column n = dy*16 + h*8 + co
+// (h = 0: hi*W_hi part, h = 1: hi*W_lo + lo*W_hi part), same canonical layout, 1536 B each.
+static void pack_tcr(Packer& pk, const float* w, int cin, ConvW& out) {
+    const int G = (cin + 7) / 8;
+    float mx = 0.f;
+    for (int i = 0; i < 8 * cin * 9; i++) mx = fmaxf(mx, fabsf(w[i]));
+    int ex = 0;
+    if (mx > 0.f) frexpf(mx, &ex);
+    const int kw = 10 - ex;
+    const float scale = ldexpf(1.f, kw);
+    out.tc_inv = ldexpf(1.f, -kw);
+    out.tcr = pk.halfs.size();
+    pk.halfs.resize(out.tcr + (size_t)G * 3 * 768, 0);
+    for (int g = 0; g < G; g++)
+        for (int dx = 0; dx < 3; dx++)
+            for (int n = 0; n < 48; n++)
+                for (int k = 0; k < 16; k++) {
+                    const int dy = n / 16, h = (n / 8) & 1, co = n & 7, ci = g * 8 + (k & 7);
+                    const float wv = ci < cin ? w[(co * cin + ci) * 9 + dy * 3 + dx] * scale : 0.f;
+                    const __half hi = __float2half_rn(wv);
+                    const __half lo = __float2half_rn((wv - __half2float(hi)) * 2048.f);
+                    __half val = __float2half_rn(0.f);
+                    if (h == 0) { if (k < 8) val = hi; }
+                    else val = (k < 8) ? lo : hi;
+                    const int byte = (n / 8) * 256 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2;
+                    uint16_t bits;
+                    memcpy(&bits, &val, 2);
+                    pk.halfs[out.tcr + (size_t)(g * 3 + dx) * 768 + byte / 2] = bits;
+                }
+}
 #endif
 
 struct Cursor {
@@ -333,8 +366,8 @@ static void pack_double_conv(Packer& pk, Cursor& cur, ConvW out[2], int cin, int
     out[1].b = pack_vec(pk, b1, cout);
     out[1].slope = out[0].slope;
 #ifdef HN_HAVE_TC
-    if (cmid == 8) pack_tc(pk, w0, cin, out[0]);
-    if (cout == 8 && cmid == 8) pack_tc(pk, w1, cmid, out[1]);
+    if (cmid == 8) { pack_tc(pk, w0, cin, out[0]); pack_tcr(pk, w0, cin, out[0]); }
+    if (cout == 8 && cmid == 8) { pack_tc(pk, w1, cmid, out[1]); pack_tcr(pk, w1, cmid, out[1]); }
 #endif
 }
 
@@ -353,6 +386,25 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
 #endif
 #ifdef HN_HAVE_TC
     if constexpr (COUT == 8) {
+        if (c->engine == 1 && a.tcr_bmat != nullptr && a.W >= c->tcr_min_res && (a.H % 2) == 0 && a.amax_in0 != nullptr) {
+            static bool tcr_attr_done[16] = {false};
+            if (!tcr_attr_done[c->device & 15]) {
+                HN_CUDA(cudaFuncSetAttribute(tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)tcr::smem_bytes(SRC)));
+                tcr_attr_done[c->device & 15] = true;
+            }
+            tcr::Args t;
+            t.inA = a.inA; t.inB = a.inB; t.sigma = a.sigma;
+            t.bmat = reinterpret_cast<const __half*>(a.tcr_bmat);
+            t.bias = a.bias; t.slope = a.slope; t.out = a.out; t.wo = a.wo; t.bo = a.bo; t.wf = a.wf; t.dwf_out = a.dwf_out;
+            t.amax_in0 = a.amax_in0; t.amax_in1 = a.amax_in1; t.amax_out = a.amax_out;
+            t.error_flag = c->err_flag; t.sigma_max = c->pml > 0 ? (float)c->sigma_max : 0.f; t.w_inv_scale = a.tc_inv;
+            t.H = a.H; t.W = a.W;
+            dim3 tgrid((a.W + tcr::CW - 1) / tcr::CW, (a.H + tcr::ROWS - 1) / tcr::ROWS, B);
+            tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI><<<tgrid, dim3(tcr::THREADS), tcr::smem_bytes(SRC), st>>>(t);
+            c->launches++;
+            return HN_OK;
+        }
         if (c->engine == 1 && a.tc_bmat != nullptr && a.H >= c->tc_min_res && (SRC == SRC_INC || a.amax_in0 != nullptr)) {
             static bool tc_attr_done[16] = {false};
             if (!tc_attr_done[c->device & 15]) {
@@ -396,6 +448,7 @@ static Conv3Args conv_args(hn_ctx* c, const ConvW& w, const float* inA, const fl
     a.H = r;
     a.W = r;
     a.tc_bmat = (w.tc != (size_t)-1 && c->tcw) ? (const void*)(c->tcw + w.tc) : nullptr;
+    a.tcr_bmat = (w.tcr != (size_t)-1 && c->tcw) ? (const void*)(c->tcw + w.tcr) : nullptr;
     a.tc_inv = w.tc_inv;
     return a;
 }
@@ -423,12 +476,15 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
         for (int i = 0; i < S_COUNT; i++) mask |= 1ull << i;
         for (int d = 0; d < kDepth; d++) mask &= ~(1ull << (S_STATE + 2 * d + cur));
         mask &= ~(1ull << S_IN6);
+        mask &= ~(1ull << (S_WF + cur));
+        mask &= ~(1ull << (S_RES + cur));
         HN_LAUNCH(reset_amax_kernel, dim3(1), dim3(64), 0, st, c->amax, mask);
         c->launches++;
     }
     // inc
     {
-        Conv3Args a = conv_args(c, W.inc[0], from_in6 ? c->in6 : c->wf, c->res, c->mid[0], c->r[0], S_IMID, from_in6 ? S_IN6 : -1);
+        Conv3Args a = conv_args(c, W.inc[0], from_in6 ? c->in6 : c->wf, c->res, c->mid[0], c->r[0], S_IMID, from_in6 ? S_IN6 : S_WF + cur,
+                                from_in6 ? -1 : S_RES + cur);
         if (from_in6) HN_TRY((launch_conv3<SRC_A8, 8, true, EPI_STORE>(c, a, B, st)));
         else HN_TRY((launch_conv3<SRC_INC, 8, true, EPI_STORE>(c, a, B, st)));
         Conv3Args a2 = conv_args(c, W.inc[1], c->mid[0], nullptr, c->x[0], c->r[0], S_X + 0, S_IMID);
@@ -490,6 +546,7 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
             d1.bo = c->wdev + W.outc.b;
             d1.wf = c->wf;
             d1.dwf_out = raw_out ? c->dwf : nullptr;
+            d1.amax_out = raw_out ? nullptr : c->amax + S_WF + nxt;
             HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_OUTC>(c, d1, B, st)));
         }
     }
@@ -498,7 +555,7 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
 
 // r = L(u) + ksq*u - src  (any of ksq/src/ssq may be null)
 static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, const float* ksq, const float* src,
-                           int src_batch, float* res, double* ssq, const int* slot) {
+                           int src_batch, float* res, double* ssq, const int* slot, unsigned* amax_out = nullptr) {
     const int n = c->n;
     const int total_rows = B * n;
     const int L = c->rows_L, CW = c->cols_CW;
@@ -512,6 +569,7 @@ static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, co
     a.res = reinterpret_cast<float2*>(res);
     a.ssq = ssq;
     a.slot = slot;
+    a.amax_out = amax_out;
     a.src_batch = src_batch;
     a.B = B;
     a.CW = CW;
@@ -523,7 +581,7 @@ static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, co
 
 static int launch_iteration(hn_ctx* c, int B, cudaStream_t st) {
     HN_TRY(launch_unet(c, B, st, false, false));
-    HN_TRY(launch_spectral(c, B, st, c->wf, c->ksq, c->src, c->src_batch, c->res, c->ssq, c->iter_dev));
+    HN_TRY(launch_spectral(c, B, st, c->wf, c->ksq, c->src, c->src_batch, c->res, c->ssq, c->iter_dev, c->amax + S_RES + (c->cur ^ 1)));
     HN_LAUNCH(advance_iter_kernel, dim3(1), dim3(32), 0, st, c->iter_dev);
     c->launches++;
     return HN_OK;
@@ -615,13 +673,14 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     A_(c->ssq1, B);
     A_(c->iter_dev, 4);
     A_(c->wdev, 65536);
-    A_(c->tcw, 81920);
+    A_(c->tcw, 163840);
     A_(c->err_flag, 4);
     A_(c->amax, 64);
 #undef A_
     if (cudaMemset(c->amax, 0, 256) != cudaSuccess) return cleanup(fail(HN_ERR_CUDA, "cudaMemset failed"));
     if (cudaMemset(c->err_flag, 0, 16) != cudaSuccess) return cleanup(fail(HN_ERR_CUDA, "cudaMemset failed"));
     if (const char* mr = getenv("HELMNET_TC_MIN_RES")) c->tc_min_res = atoi(mr);
+    if (const char* mr = getenv("HELMNET_TCR_MIN_RES")) c->tcr_min_res = atoi(mr);
     if (const char* en = getenv("HELMNET_ENGINE")) c->engine = atoi(en) == 1 ? 1 : 0;
 #ifdef HN_EMU
     c->engine = 0;
@@ -694,7 +753,7 @@ int hn_load_weights(hn_ctx* c, const float* host_blob, size_t n_floats) {
     HN_CUDA(cudaDeviceSynchronize());
 #endif
     HN_CUDA(cudaMemcpy(c->wdev, pk.blob.data(), pk.blob.size() * 4, cudaMemcpyHostToDevice));
-    if (pk.halfs.size() > 81920) return fail(HN_ERR_STATE, "tensor-core weight images exceed the reserved buffer");
+    if (pk.halfs.size() > 163840) return fail(HN_ERR_STATE, "tensor-core weight images exceed the reserved buffer");
     if (!pk.halfs.empty()) HN_CUDA(cudaMemcpy(c->tcw, pk.halfs.data(), pk.halfs.size() * 2, cudaMemcpyHostToDevice));
     c->weights_set = true;
     return HN_OK;
@@ -729,9 +788,11 @@ int hn_reset(hn_ctx* c, const float* d_sos, int batch, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int hw = c->n * c->n;
     const size_t total = (size_t)batch * hw;
+    HN_CUDA(cudaMemsetAsync(c->amax + S_WF + c->cur, 0, sizeof(unsigned), st));
+    HN_CUDA(cudaMemsetAsync(c->amax + S_RES + c->cur, 0, sizeof(unsigned), st));
     HN_LAUNCH(reset_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_sos, c->ksq, reinterpret_cast<float2*>(c->wf),
               reinterpret_cast<float2*>(c->res), reinterpret_cast<const float2*>(c->src), c->src_batch, (float)c->omega, hw,
-              total);
+              total, c->amax + S_RES + c->cur);
     c->launches++;
     for (int d = 0; d < kDepth; d++) {
         HN_CUDA(cudaMemsetAsync(c->state[d][c->cur], 0, (size_t)batch * c->r[d] * c->r[d] * 8, st));
@@ -752,11 +813,15 @@ int hn_set_state(hn_ctx* c, const float* d_wf, const float* d_res, const float* 
     const int hw = c->n * c->n;
     const size_t total = (size_t)batch * hw;
     if (d_wf) {
-        HN_LAUNCH(nchw2_to_c2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_wf, reinterpret_cast<float2*>(c->wf), hw, total);
+        HN_CUDA(cudaMemsetAsync(c->amax + S_WF + c->cur, 0, sizeof(unsigned), st));
+        HN_LAUNCH(nchw2_to_c2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_wf, reinterpret_cast<float2*>(c->wf), hw, total,
+                  c->amax + S_WF + c->cur);
         c->launches++;
     }
     if (d_res) {
-        HN_LAUNCH(nchw2_to_c2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_res, reinterpret_cast<float2*>(c->res), hw, total);
+        HN_CUDA(cudaMemsetAsync(c->amax + S_RES + c->cur, 0, sizeof(unsigned), st));
+        HN_LAUNCH(nchw2_to_c2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_res, reinterpret_cast<float2*>(c->res), hw, total,
+                  c->amax + S_RES + c->cur);
         c->launches++;
     }
     if (d_ksq) HN_CUDA(cudaMemcpyAsync(c->ksq, d_ksq, total * 4, cudaMemcpyDeviceToDevice, st));
@@ -928,7 +993,7 @@ int hn_residual(hn_ctx* c, const float* d_x, const float* d_ksq, float* d_out, f
     cudaStream_t st = (cudaStream_t)stream;
     const int hw = c->n * c->n;
     const size_t total = (size_t)batch * hw;
-    HN_LAUNCH(nchw2_to_c2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_x, reinterpret_cast<float2*>(c->tmp2), hw, total);
+    HN_LAUNCH(nchw2_to_c2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_x, reinterpret_cast<float2*>(c->tmp2), hw, total, (unsigned*)nullptr);
     HN_CUDA(cudaMemsetAsync(c->ssq1, 0, (size_t)batch * sizeof(double), st));
     HN_TRY(launch_spectral(c, batch, st, c->tmp2, d_ksq ? d_ksq : c->ksq, c->src, c->src_batch, c->tmp2b, c->ssq1, c->iter_dev + 1));
     HN_LAUNCH(c2_to_nchw2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, reinterpret_cast<const float2*>(c->tmp2b), d_out, hw,
@@ -948,7 +1013,7 @@ int hn_laplacian(hn_ctx* c, const float* d_x, float* d_out, int batch, void* str
     cudaStream_t st = (cudaStream_t)stream;
     const int hw = c->n * c->n;
     const size_t total = (size_t)batch * hw;
-    HN_LAUNCH(nchw2_to_c2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_x, reinterpret_cast<float2*>(c->tmp2), hw, total);
+    HN_LAUNCH(nchw2_to_c2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, d_x, reinterpret_cast<float2*>(c->tmp2), hw, total, (unsigned*)nullptr);
     HN_TRY(launch_spectral(c, batch, st, c->tmp2, nullptr, nullptr, 1, c->tmp2b, nullptr, c->iter_dev + 1));
     HN_LAUNCH(c2_to_nchw2_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, st, reinterpret_cast<const float2*>(c->tmp2b), d_out, hw,
               total, (size_t)2 * hw, (size_t)hw);
@@ -1038,7 +1103,8 @@ int hn_profile_iteration(hn_ctx* c, float out_ms[2], void* stream) {
     int rc = launch_unet(c, c->batch, st, false, false);
     if (rc == HN_OK) {
         cudaEventRecord(e1, st);
-        rc = launch_spectral(c, c->batch, st, c->wf, c->ksq, c->src, c->src_batch, c->res, c->ssq1, c->iter_dev + 1);
+        rc = launch_spectral(c, c->batch, st, c->wf, c->ksq, c->src, c->src_batch, c->res, c->ssq1, c->iter_dev + 1,
+                             c->amax + S_RES + (c->cur ^ 1));
     }
     if (rc == HN_OK) {
         cudaEventRecord(e2, st);

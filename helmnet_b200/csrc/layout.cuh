@@ -10,11 +10,16 @@ namespace hn {
 constexpr int LAY_THREADS = 256;
 
 // [B,2,H,W] -> float2 [B,H,W]
-__global__ void nchw2_to_c2_kernel(const float* __restrict__ in, float2* __restrict__ out, int hw, size_t total) {
+__global__ void nchw2_to_c2_kernel(const float* __restrict__ in, float2* __restrict__ out, int hw, size_t total,
+                                   unsigned* amax_out) {
+    float lmax = 0.f;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t b = i / hw, p = i - b * hw;
-        out[i] = make_float2(in[(b * 2) * hw + p], in[(b * 2 + 1) * hw + p]);
+        const float2 v = make_float2(in[(b * 2) * hw + p], in[(b * 2 + 1) * hw + p]);
+        out[i] = v;
+        lmax = fmaxf(lmax, fmaxf(fabsf(v.x), fabsf(v.y)));
     }
+    publish_amax(amax_out, lmax);
 }
 // float2 [B,H,W] -> [B,2,H,W] with an output batch stride (in floats) so that per-level hidden states can be
 // scattered into the flattened [B,2,S] layout of HybridNet.flatten_state (architectures.py:419-423).
@@ -52,7 +57,8 @@ __global__ void src_strided_to_c2_kernel(const float* __restrict__ in, float2* _
 // get_initials + initial residual: k_sq = (omega/sos)^2, wf = 0, res = L(0) + k_sq*0 - source = -source
 __global__ void reset_kernel(const float* __restrict__ sos, float* __restrict__ ksq, float2* __restrict__ wf,
                              float2* __restrict__ res, const float2* __restrict__ src, int src_batch, float omega, int hw,
-                             size_t total) {
+                             size_t total, unsigned* amax_res) {
+    float lmax = 0.f;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t b = i / hw, p = i - b * hw;
         const float q = omega / sos[i];
@@ -60,7 +66,9 @@ __global__ void reset_kernel(const float* __restrict__ sos, float* __restrict__ 
         wf[i] = make_float2(0.f, 0.f);
         const float2 s = src[(src_batch > 1 ? b * hw : 0) + p];
         res[i] = make_float2(0.f - s.x, 0.f - s.y);
+        lmax = fmaxf(lmax, fmaxf(fabsf(s.x), fabsf(s.y)));
     }
+    publish_amax(amax_res, lmax);
 }
 // [B,6,H,W] -> NHWC8 (channels 6,7 zero): input of HybridNet.forward when called directly
 __global__ void nchw6_to_nhwc8_kernel(const float* __restrict__ in, float* __restrict__ out, int hw, size_t total,

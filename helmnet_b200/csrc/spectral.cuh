@@ -170,6 +170,7 @@ struct ColsArgs {
     float2* res;          // [B][n][n]
     double* ssq;          // [slots][B] or null
     const int* slot;      // device scalar: which ssq slot (iteration index)
+    unsigned* amax_out;   // running max |res| slot (publish_amax) or null
     int src_batch, B, CW;
 };
 
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) spectral_cols_kernel(SpecTables 
     }
     __syncthreads();
     const float2* E = axis_operator(A, B, C, S, nc, lp, tw, t);
-    float part = 0.f;
+    float part = 0.f, lmax = 0.f;
     for (int it = threadIdx.x; it < n * CW; it += blockDim.x) {
         const int i = it / CW, c = it - i * CW;
         if (c >= nc) continue;
@@ -212,7 +213,9 @@ __global__ void __launch_bounds__(SPEC_THREADS) spectral_cols_kernel(SpecTables 
         a.res[p] = r;
         part = fmaf(r.x, r.x, part);
         part = fmaf(r.y, r.y, part);
+        lmax = fmaxf(lmax, fmaxf(fabsf(r.x), fabsf(r.y)));
     }
+    publish_amax(a.amax_out, lmax);
     if (a.ssq != nullptr) {
         part = warp_sum(part);
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;

@@ -22,14 +22,16 @@ __device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity) {
 }
 
 // mode: N of the MMA; nacc: number of accumulators rotated over; nmma: MMAs per measurement; kchunks: K=16 fixed
-__global__ void bench(int N, int nacc, int nmma, int shiftmode, long long* out, int nld) {
+__global__ void bench(int N, int nacc, int nmma, int shiftmode, long long* out, int nld, int commit_every) {
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bar2;
     __shared__ uint32_t tslot;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     asm volatile("fence.proxy.async.shared::cta;");
@@ -48,7 +50,13 @@ __global__ void bench(int N, int nacc, int nmma, int shiftmode, long long* out, 
         uint64_t da[9], db = make_desc(b0, 128, 256);
         for (int t = 0; t < 9; t++) da[t] = make_desc(a0 + (shiftmode ? t * 16 : 0), 17536, 128);
         t0 = clock64();
-        if (nacc == 1) {
+        if (commit_every > 0) {
+            for (int i = 0; i < nmma; i += 3) {
+#pragma unroll
+                for (int t = 0; t < 3; t++) mma(tb, da[t], db, idesc, 1);
+                if ((i / 3) % commit_every == 0) commit(&bar2);
+            }
+        } else if (nacc == 1) {
             for (int i = 0; i < nmma; i += 9) {
 #pragma unroll
                 for (int t = 0; t < 9; t++) mma(tb, da[t], db, idesc, 1);
@@ -95,15 +103,15 @@ int main() {
     cudaMalloc(&d, 148 * 4 * 8);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
     const int nmma = 1152;
-    struct { int N, nacc, shift, grid; } cfg[] = {{16, 1, 0, 1}, {16, 1, 1, 1}, {16, 4, 1, 1}, {8, 1, 1, 1}, {8, 4, 1, 1}, {32, 1, 1, 1}, {32, 4, 1, 1},
+    struct { int N, nacc, shift, grid, ce; } cfg[] = {{16, 1, 1, 1, 1}, {16, 1, 1, 1, 2}, {16, 1, 1, 1, 4}, {16, 1, 1, 1, 16}, {48, 1, 1, 1, 1}, {48, 1, 1, 1, 4},{16, 1, 0, 1}, {16, 1, 1, 1}, {16, 4, 1, 1}, {8, 1, 1, 1}, {8, 4, 1, 1}, {32, 1, 1, 1}, {32, 4, 1, 1},
                                                    {64, 4, 0, 1}, {128, 1, 0, 1}, {128, 4, 0, 1}, {256, 1, 0, 1}, {16, 4, 1, 148}, {16, 4, 1, 296}, {16, 4, 1, 592}};
     for (auto& c : cfg) {
         cudaMemset(d, 0, 148 * 32);
-        bench<<<c.grid, 128, 48 * 1024>>>(c.N, c.nacc, nmma, c.shift, d, 256);
+        bench<<<c.grid, 128, 48 * 1024>>>(c.N, c.nacc, nmma, c.shift, d, 256, c.ce);
         cudaError_t e = cudaDeviceSynchronize();
         long long h[8];
         cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
-        printf("N=%3d nacc=%d shift=%d grid=%3d : %s  %.1f cyc/MMA   ld.x16: %.1f cyc/ld (per warp, 4 warps)\n", c.N, c.nacc, c.shift, c.grid,
+        printf("N=%3d nacc=%d shift=%d grid=%3d commit_every_3mma_x%d : %s  %.1f cyc/MMA   ld.x16: %.1f cyc/ld (per warp, 4 warps)\n", c.N, c.nacc, c.shift, c.grid, c.ce,
                cudaGetErrorString(e), (double)h[0] / nmma, (double)h[1] / 256);
     }
     return 0;
