@@ -26,7 +26,9 @@
 // Every ring advances in steps of TWO image rows (one barrier round trip per row pair): the roles are latency bound
 // per step (mbarrier wake-ups, tcgen05.ld/st round trips, one serial MMA-issuing thread), not throughput bound,
 // so halving the number of steps is what moved the kernel (profiles/r1_ncu_tcr_*.txt).
-// Two CTAs per SM (2 x 256 TMEM columns).
+// The kernel is PERSISTENT: 2 CTAs per SM (2 x 256 TMEM columns) walk over all strips of all samples with running
+// ring counters, so TMEM allocation, barrier setup, accumulator zeroing and pipeline fill/drain are paid once per
+// CTA instead of once per strip (32-row strips cost 15 % in setup/drain when launched one CTA per strip).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -48,7 +50,7 @@ constexpr int PROD_WARPS = 10, EPI_WARPS = 4;
 constexpr int MMA_WARP = PROD_WARPS;
 constexpr int TMA_WARP = PROD_WARPS + 1 + EPI_WARPS;
 constexpr int THREADS = (PROD_WARPS + 1 + EPI_WARPS + 1) * 32;   // 512
-constexpr int ROWS = 32;           // output rows per CTA
+constexpr int ROWS = 32;           // output rows per strip
 constexpr int ST8 = 4224;          // staging bytes of one 8-channel row segment (130 px x 32 B, padded)
 constexpr int ST2 = 1152;          // staging bytes of one 2-channel row segment (132 px x 8 B starting at x0-2, padded)
 constexpr int BROW_BYTES = 1536;   // one (group, dx) B operand: 48 x 16 fp16
@@ -85,7 +87,24 @@ struct Args {
     float sigma_max;            // INC: max of the sigma profile
     float w_inv_scale;
     int H, W;
+    int nsx, nsy, total_strips;  // strips per row / per column of one sample, and over the whole batch
 };
+
+struct Strip {
+    int x0, y0, R, NP;
+    size_t img;
+};
+__device__ __forceinline__ Strip strip_of(int st, const Args& a) {
+    Strip g;
+    const int sx = st % a.nsx, r = st / a.nsx;
+    const int sy = r % a.nsy, b = r / a.nsy;
+    g.x0 = sx * CW;
+    g.y0 = sy * ROWS;
+    g.R = min(ROWS, a.H - g.y0);       // even: H and ROWS are even
+    g.NP = (g.R + 2) / 2;              // input row pairs incl. halo; input row k = 2j + t is image row y0 - 1 + k
+    g.img = (size_t)b * a.H * a.W;
+    return g;
+}
 
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
@@ -116,7 +135,8 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
     constexpr int G = groups_of(SRC);
     constexpr int SRP = op_ring(SRC) / 2;      // operand ring depth in row pairs
     constexpr int NSP = stage_ring(SRC) / 2;   // staging ring depth in row pairs
-    constexpr int NPB = 8;                     // pair barriers: 16 accumulator units = 8 row pairs
+    constexpr int NPB = 8;                     // output-pair barriers: 16 accumulator units = 8 row pairs
+    constexpr int NDB = 16;                    // input-pair completion barriers (deeper: halo pairs make input run ahead)
     constexpr uint32_t kIdescBase = (1u << 4) | ((128u >> 4) << 24);   // f16 x f16 -> f32, both K-major, M=128; N field added per MMA
     extern __shared__ __align__(128) uint8_t smem_tcr[];
     uint8_t* stage = smem_tcr;                                                    // [NSP][2 rows] fp32 row segments (TMA destination)
@@ -124,8 +144,8 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
     uint8_t* bsm = ring + (size_t)SRP * 2 * slot_bytes(SRC);                      // [G][3][1536]
     uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + G * 3 * BROW_BYTES);
     uint64_t* smem_full = bars;                  // [SRP]  2 x 136 converter arrivals (operand rows of a pair written)
-    uint64_t* pair_done = smem_full + SRP;       // [NPB]  1 (tcgen05.commit): MMAs of input row pair j done
-    uint64_t* tmem_empty = pair_done + NPB;      // [NPB]  128 epilogue arrivals: accumulators of output pair read + zeroed
+    uint64_t* pair_done = smem_full + SRP;       // [NDB]  1 (tcgen05.commit): MMAs of input row pair j done
+    uint64_t* tmem_empty = pair_done + NDB;      // [NPB]  128 epilogue arrivals: accumulators of output pair read + zeroed
     uint64_t* stage_full = tmem_empty + NPB;     // [NSP]  1 arrival + TMA transaction bytes
     uint64_t* stage_empty = stage_full + NSP;    // [NSP]  2 x 136 converter arrivals
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_empty + NSP);
@@ -133,10 +153,6 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = a.H, W = a.W;
-    const int x0 = blockIdx.x * CW, y0 = blockIdx.y * ROWS, b = blockIdx.z;
-    const int R = min(ROWS, H - y0);       // output rows of this strip (even: H and ROWS are even)
-    const int NP = (R + 2) / 2;            // input row pairs incl. halo; input row k = 2j + t is image row y0 - 1 + k
-    const size_t img = (size_t)b * H * W;
 
     // ---- setup ------------------------------------------------------------------------------------------
     if (warp == MMA_WARP) {
@@ -145,10 +161,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
     }
     if (tid == 0) {
         for (int i = 0; i < SRP; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(smem_full + i)), "r"(2 * PS));
-        for (int i = 0; i < NPB; i++) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(pair_done + i)));
+        for (int i = 0; i < NDB; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(pair_done + i)));
+        for (int i = 0; i < NPB; i++)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(tmem_empty + i)), "r"(EPI_WARPS * 32));
-        }
         for (int i = 0; i < NSP; i++) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(stage_full + i)));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(stage_empty + i)), "r"(2 * PS));
@@ -196,43 +211,50 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
     const float mult = __uint_as_float((uint32_t)(267 - e) << 23);
     const float out_scale = __uint_as_float((uint32_t)(e - 13) << 23) * a.w_inv_scale;
 
-    // valid pixel range of a row segment: 8-channel sources start at x0-1, 2-channel ones at x0-2 (16-byte alignment)
-    const int lo8 = max(0, x0 - 1), hi8 = min(W, x0 + CW + 1);
-    const int lo2 = max(0, x0 - 2), hi2 = min(W, x0 + CW + 2);
-
+    // Running counters (identical in every role because all roles walk the same strips in the same order):
+    //   gj = input row pairs processed so far, go = output rows processed so far.
     bool ok = true;
     if (warp == TMA_WARP) {
         // =============================== TMA issuer ===============================================================
         if (lane == 0) {
-            const uint32_t b8 = (uint32_t)(hi8 - lo8) * 32u, b2 = (uint32_t)(hi2 - lo2) * 8u;
-            const uint32_t row_bytes = SRC == SRC_INC ? 2 * b2 : SRC == SRC_A8 ? b8 : SRC == SRC_A8_B8 ? 2 * b8 : b8 + b2;
+            int gj = 0;
 #pragma unroll 1
-            for (int j = 0; j < NP; j++) {
-                const int sidx = j % NSP;
-                if (!mbar_wait(stage_empty + sidx, ((uint32_t)(j / NSP) & 1u) ^ 1u)) { ok = false; break; }
-                const int gy0 = y0 - 1 + 2 * j;
-                const bool v0 = gy0 >= 0 && gy0 < H, v1 = gy0 + 1 >= 0 && gy0 + 1 < H;
-                if (!v0 && !v1) {
-                    mbar_arrive(stage_full + sidx);            // zero padding rows only: nothing to copy
-                    continue;
-                }
-                mbar_arrive_expect_tx(stage_full + sidx, ((uint32_t)v0 + (uint32_t)v1) * row_bytes);
+            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
+                const Strip g = strip_of(st, a);
+                const int x0 = g.x0;
+                // valid pixel range of a row segment: 8-channel sources start at x0-1, 2-channel ones at x0-2 (16-byte alignment)
+                const int lo8 = max(0, x0 - 1), hi8 = min(W, x0 + CW + 1);
+                const int lo2 = max(0, x0 - 2), hi2 = min(W, x0 + CW + 2);
+                const uint32_t b8 = (uint32_t)(hi8 - lo8) * 32u, b2 = (uint32_t)(hi2 - lo2) * 8u;
+                const uint32_t row_bytes = SRC == SRC_INC ? 2 * b2 : SRC == SRC_A8 ? b8 : SRC == SRC_A8_B8 ? 2 * b8 : b8 + b2;
+#pragma unroll 1
+                for (int j = 0; j < g.NP; j++, gj++) {
+                    const int sidx = gj % NSP;
+                    if (!mbar_wait(stage_empty + sidx, ((uint32_t)(gj / NSP) & 1u) ^ 1u)) { ok = false; break; }
+                    const int gy0 = g.y0 - 1 + 2 * j;
+                    const bool v0 = gy0 >= 0 && gy0 < H, v1 = gy0 + 1 >= 0 && gy0 + 1 < H;
+                    if (!v0 && !v1) {
+                        mbar_arrive(stage_full + sidx);            // zero padding rows only: nothing to copy
+                        continue;
+                    }
+                    mbar_arrive_expect_tx(stage_full + sidx, ((uint32_t)v0 + (uint32_t)v1) * row_bytes);
 #pragma unroll
-                for (int t = 0; t < 2; t++) {
-                    if (!(t == 0 ? v0 : v1)) continue;
-                    uint8_t* dst = stage + (size_t)(sidx * 2 + t) * stage_bytes(SRC);
-                    const size_t rowpix = img + (size_t)(gy0 + t) * W;
-                    if constexpr (SRC == SRC_INC) {
-                        tma_load_1d(dst + (lo2 - (x0 - 2)) * 8, a.inA + (rowpix + lo2) * 2, b2, stage_full + sidx);
-                        tma_load_1d(dst + ST2 + (lo2 - (x0 - 2)) * 8, a.inB + (rowpix + lo2) * 2, b2, stage_full + sidx);
-                    } else if constexpr (SRC == SRC_A8) {
-                        tma_load_1d(dst + (lo8 - (x0 - 1)) * 32, a.inA + (rowpix + lo8) * 8, b8, stage_full + sidx);
-                    } else if constexpr (SRC == SRC_A8_B8) {
-                        tma_load_1d(dst + (lo8 - (x0 - 1)) * 32, a.inA + (rowpix + lo8) * 8, b8, stage_full + sidx);
-                        tma_load_1d(dst + ST8 + (lo8 - (x0 - 1)) * 32, a.inB + (rowpix + lo8) * 8, b8, stage_full + sidx);
-                    } else {   // SRC_A8_B2
-                        tma_load_1d(dst + (lo8 - (x0 - 1)) * 32, a.inA + (rowpix + lo8) * 8, b8, stage_full + sidx);
-                        tma_load_1d(dst + ST8 + (lo2 - (x0 - 2)) * 8, a.inB + (rowpix + lo2) * 2, b2, stage_full + sidx);
+                    for (int t = 0; t < 2; t++) {
+                        if (!(t == 0 ? v0 : v1)) continue;
+                        uint8_t* dst = stage + (size_t)(sidx * 2 + t) * stage_bytes(SRC);
+                        const size_t rowpix = g.img + (size_t)(gy0 + t) * W;
+                        if constexpr (SRC == SRC_INC) {
+                            tma_load_1d(dst + (lo2 - (x0 - 2)) * 8, a.inA + (rowpix + lo2) * 2, b2, stage_full + sidx);
+                            tma_load_1d(dst + ST2 + (lo2 - (x0 - 2)) * 8, a.inB + (rowpix + lo2) * 2, b2, stage_full + sidx);
+                        } else if constexpr (SRC == SRC_A8) {
+                            tma_load_1d(dst + (lo8 - (x0 - 1)) * 32, a.inA + (rowpix + lo8) * 8, b8, stage_full + sidx);
+                        } else if constexpr (SRC == SRC_A8_B8) {
+                            tma_load_1d(dst + (lo8 - (x0 - 1)) * 32, a.inA + (rowpix + lo8) * 8, b8, stage_full + sidx);
+                            tma_load_1d(dst + ST8 + (lo8 - (x0 - 1)) * 32, a.inB + (rowpix + lo8) * 8, b8, stage_full + sidx);
+                        } else {   // SRC_A8_B2
+                            tma_load_1d(dst + (lo8 - (x0 - 1)) * 32, a.inA + (rowpix + lo8) * 8, b8, stage_full + sidx);
+                            tma_load_1d(dst + ST8 + (lo2 - (x0 - 2)) * 8, a.inB + (rowpix + lo2) * 2, b2, stage_full + sidx);
+                        }
                     }
                 }
             }
@@ -242,57 +264,62 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
         // =============================== converters ===============================================================
         const int team = tid / TEAM, p = tid - team * TEAM;     // team t converts row 2j + t; p: position in the row (136 active)
         if (p < PS) {
-            const int gx = x0 - 1 + p;
-            const bool colok = (p < CW + 2) && gx >= 0 && gx < W;
+            int gj = 0;
 #pragma unroll 1
-            for (int j = 0; j < NP; j++) {
-                const int sidx = j % NSP, s = j % SRP;
-                const int gy = y0 - 1 + 2 * j + team;
-                float g0[8];
-                float g1[G == 2 ? 8 : 1];
+            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
+                const Strip g = strip_of(st, a);
+                const int gx = g.x0 - 1 + p;
+                const bool colok = (p < CW + 2) && gx >= 0 && gx < W;
+#pragma unroll 1
+                for (int j = 0; j < g.NP; j++, gj++) {
+                    const int sidx = gj % NSP, s = gj % SRP;
+                    const int gy = g.y0 - 1 + 2 * j + team;
+                    float g0[8];
+                    float g1[G == 2 ? 8 : 1];
 #pragma unroll
-                for (int c = 0; c < 8; c++) g0[c] = 0.f;
+                    for (int c = 0; c < 8; c++) g0[c] = 0.f;
 #pragma unroll
-                for (int c = 0; c < (G == 2 ? 8 : 1); c++) g1[c] = 0.f;
-                if (!mbar_wait(stage_full + sidx, (uint32_t)(j / NSP) & 1u)) { ok = false; break; }
-                if (colok && gy >= 0 && gy < H) {
-                    const uint8_t* src = stage + (size_t)(sidx * 2 + team) * stage_bytes(SRC);
-                    if constexpr (SRC == SRC_INC) {
-                        const float2 u2 = *reinterpret_cast<const float2*>(src + (p + 1) * 8);
-                        const float2 r2 = *reinterpret_cast<const float2*>(src + ST2 + (p + 1) * 8);
-                        g0[0] = u2.x; g0[1] = u2.y;
-                        g0[2] = 1e3f * r2.x; g0[3] = 1e3f * r2.y;                             // hybridnet.py:566
-                        g0[4] = __ldg(a.sigma + gx); g0[5] = __ldg(a.sigma + gy);
-                    } else {
-                        const float4 q0 = *reinterpret_cast<const float4*>(src + p * 32), q1 = *reinterpret_cast<const float4*>(src + p * 32 + 16);
-                        g0[0] = q0.x; g0[1] = q0.y; g0[2] = q0.z; g0[3] = q0.w;
-                        g0[4] = q1.x; g0[5] = q1.y; g0[6] = q1.z; g0[7] = q1.w;
-                        if constexpr (SRC == SRC_A8_B8) {
-                            const float4 s0 = *reinterpret_cast<const float4*>(src + ST8 + p * 32);
-                            const float4 s1 = *reinterpret_cast<const float4*>(src + ST8 + p * 32 + 16);
-                            g1[0] = s0.x; g1[1] = s0.y; g1[2] = s0.z; g1[3] = s0.w;
-                            g1[4] = s1.x; g1[5] = s1.y; g1[6] = s1.z; g1[7] = s1.w;
-                        } else if constexpr (SRC == SRC_A8_B2) {
-                            const float2 sv = *reinterpret_cast<const float2*>(src + ST8 + (p + 1) * 8);
-                            g1[0] = sv.x; g1[1] = sv.y;
+                    for (int c = 0; c < (G == 2 ? 8 : 1); c++) g1[c] = 0.f;
+                    if (!mbar_wait(stage_full + sidx, (uint32_t)(gj / NSP) & 1u)) { ok = false; break; }
+                    if (colok && gy >= 0 && gy < H) {
+                        const uint8_t* src = stage + (size_t)(sidx * 2 + team) * stage_bytes(SRC);
+                        if constexpr (SRC == SRC_INC) {
+                            const float2 u2 = *reinterpret_cast<const float2*>(src + (p + 1) * 8);
+                            const float2 r2 = *reinterpret_cast<const float2*>(src + ST2 + (p + 1) * 8);
+                            g0[0] = u2.x; g0[1] = u2.y;
+                            g0[2] = 1e3f * r2.x; g0[3] = 1e3f * r2.y;                             // hybridnet.py:566
+                            g0[4] = __ldg(a.sigma + gx); g0[5] = __ldg(a.sigma + gy);
+                        } else {
+                            const float4 q0 = *reinterpret_cast<const float4*>(src + p * 32), q1 = *reinterpret_cast<const float4*>(src + p * 32 + 16);
+                            g0[0] = q0.x; g0[1] = q0.y; g0[2] = q0.z; g0[3] = q0.w;
+                            g0[4] = q1.x; g0[5] = q1.y; g0[6] = q1.z; g0[7] = q1.w;
+                            if constexpr (SRC == SRC_A8_B8) {
+                                const float4 s0 = *reinterpret_cast<const float4*>(src + ST8 + p * 32);
+                                const float4 s1 = *reinterpret_cast<const float4*>(src + ST8 + p * 32 + 16);
+                                g1[0] = s0.x; g1[1] = s0.y; g1[2] = s0.z; g1[3] = s0.w;
+                                g1[4] = s1.x; g1[5] = s1.y; g1[6] = s1.z; g1[7] = s1.w;
+                            } else if constexpr (SRC == SRC_A8_B2) {
+                                const float2 sv = *reinterpret_cast<const float2*>(src + ST8 + (p + 1) * 8);
+                                g1[0] = sv.x; g1[1] = sv.y;
+                            }
                         }
                     }
+                    // operand pair slot s was last used by pair gj - SRP: free once that pair's MMAs completed
+                    if (gj >= SRP && !mbar_wait(pair_done + ((gj - SRP) & (NDB - 1)), (uint32_t)((gj - SRP) / NDB) & 1u)) { ok = false; break; }
+                    uint4* slot = reinterpret_cast<uint4*>(ring + (size_t)(s * 2 + team) * slot_bytes(SRC));
+                    uint4 hi, lo;
+                    tc::split8(g0, mult, hi, lo);
+                    slot[p] = hi;
+                    slot[PS + p] = lo;
+                    if constexpr (G == 2) {
+                        tc::split8(g1, mult, hi, lo);
+                        slot[2 * PS + p] = hi;
+                        slot[3 * PS + p] = lo;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;");
+                    mbar_arrive(smem_full + s);
+                    mbar_arrive(stage_empty + sidx);             // staging rows consumed (their values went through registers)
                 }
-                // operand pair slot s was last used by pair j - SRP: free once that pair's MMAs completed
-                if (j >= SRP && !mbar_wait(pair_done + ((j - SRP) & (NPB - 1)), (uint32_t)((j - SRP) / NPB) & 1u)) { ok = false; break; }
-                uint4* slot = reinterpret_cast<uint4*>(ring + (size_t)(s * 2 + team) * slot_bytes(SRC));
-                uint4 hi, lo;
-                tc::split8(g0, mult, hi, lo);
-                slot[p] = hi;
-                slot[PS + p] = lo;
-                if constexpr (G == 2) {
-                    tc::split8(g1, mult, hi, lo);
-                    slot[2 * PS + p] = hi;
-                    slot[3 * PS + p] = lo;
-                }
-                asm volatile("fence.proxy.async.shared::cta;");
-                mbar_arrive(smem_full + s);
-                mbar_arrive(stage_empty + sidx);             // staging rows consumed (their values went through registers)
             }
         }
     } else if (warp == MMA_WARP) {
@@ -313,38 +340,27 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
                 }
             constexpr uint32_t kSlot16 = (uint32_t)(slot_bytes(SRC) >> 4);      // operand row pitch in 16-byte units
             constexpr uint32_t kIdesc48 = kIdescBase | (6u << 17);
+            int gj = 0, go = 0;
 #pragma unroll 1
-            for (int j = 0; j < NP; j++) {
-                const int s = j % SRP;
-                if (!mbar_wait(smem_full + s, (uint32_t)(j / SRP) & 1u)) { ok = false; break; }
-                // the accumulators this pair touches first (output rows 2j, 2j+1) must have been drained and zeroed
-                if (2 * j < R && !mbar_wait(tmem_empty + (j & (NPB - 1)), ((uint32_t)(j / NPB) & 1u) ^ 1u)) { ok = false; break; }
-                asm volatile("tcgen05.fence::after_thread_sync;");
+            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
+                const Strip gs = strip_of(st, a);
+                const int R = gs.R;
+#pragma unroll 1
+                for (int j = 0; j < gs.NP; j++, gj++) {
+                    const int s = gj % SRP;
+                    if (!mbar_wait(smem_full + s, (uint32_t)(gj / SRP) & 1u)) { ok = false; break; }
+                    // the accumulators this pair touches first (output rows 2j, 2j+1) must have been drained and zeroed
+                    const int gop = (go >> 1) + j;           // global output pair index
+                    if (2 * j < R && !mbar_wait(tmem_empty + (gop & (NPB - 1)), ((uint32_t)(gop / NPB) & 1u) ^ 1u)) { ok = false; break; }
+                    asm volatile("tcgen05.fence::after_thread_sync;");
 #pragma unroll
-                for (int t = 0; t < 2; t++) {
-                    const int k = 2 * j + t;
-                    const uint64_t soff = (uint64_t)((uint32_t)(s * 2 + t) * kSlot16);
-                    if (k >= 2 && k < R && (k & 15) >= 2) {
-                        // common case: three adjacent accumulators (rows k, k-1, k-2), one N = 48 MMA per (group, dx)
-                        const uint32_t d_tmem = tmem_base + (uint32_t)((15 - (k & 15)) * NC);
-#pragma unroll
-                        for (int g = 0; g < G; g++)
-#pragma unroll
-                            for (int dx = 0; dx < 3; dx++)
-                                asm volatile(
-                                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-                                    "l"(da0[g][dx] + soff), "l"(db0[g][dx]), "r"(kIdesc48), "r"(1u));
-                    } else {
-                        // strip edges (fewer than three live output rows) and the ring wrap: contiguous sub-ranges of dy
-                        const int dlo = max(0, k - (R - 1)), dhi = min(2, k);
-                        int dy = dlo;
-                        while (dy <= dhi) {
-                            const int u = 15 - ((k - dy) & 15);
-                            int len = 1;
-                            while (dy + len <= dhi && u + len <= 15) len++;
-                            const uint32_t d_tmem = tmem_base + (uint32_t)(u * NC);
-                            const uint32_t idesc = kIdescBase | ((uint32_t)(2 * len) << 17);          // N = 16 * len
+                    for (int t = 0; t < 2; t++) {
+                        const int k = 2 * j + t;
+                        const int gk = go + k;               // global index of output row y = k (dy = 0)
+                        const uint64_t soff = (uint64_t)((uint32_t)(s * 2 + t) * kSlot16);
+                        if (k >= 2 && k < R && (gk & 15) >= 2) {
+                            // common case: three adjacent accumulators (rows k, k-1, k-2), one N = 48 MMA per (group, dx)
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((15 - (gk & 15)) * NC);
 #pragma unroll
                             for (int g = 0; g < G; g++)
 #pragma unroll
@@ -352,85 +368,116 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
                                     asm volatile(
                                         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-                                        "l"(da0[g][dx] + soff), "l"(db0[g][dx] + (uint64_t)(dy * 32)), "r"(idesc), "r"(1u));
-                            dy += len;
+                                        "l"(da0[g][dx] + soff), "l"(db0[g][dx]), "r"(kIdesc48), "r"(1u));
+                        } else {
+                            // strip edges (fewer than three live output rows) and the ring wrap: contiguous sub-ranges of dy
+                            const int dlo = max(0, k - (R - 1)), dhi = min(2, k);
+                            int dy = dlo;
+                            while (dy <= dhi) {
+                                const int u = 15 - ((gk - dy) & 15);
+                                int len = 1;
+                                while (dy + len <= dhi && u + len <= 15) len++;
+                                const uint32_t d_tmem = tmem_base + (uint32_t)(u * NC);
+                                const uint32_t idesc = kIdescBase | ((uint32_t)(2 * len) << 17);          // N = 16 * len
+#pragma unroll
+                                for (int g = 0; g < G; g++)
+#pragma unroll
+                                    for (int dx = 0; dx < 3; dx++)
+                                        asm volatile(
+                                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                                            "l"(da0[g][dx] + soff), "l"(db0[g][dx] + (uint64_t)(dy * 32)), "r"(idesc), "r"(1u));
+                                dy += len;
+                            }
                         }
                     }
+                    // one commit per pair: frees operand pair slot s AND publishes the accumulators
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc::smem_u32(pair_done + (gj & (NDB - 1)))));
                 }
-                // one commit per pair: frees operand pair slot s AND publishes the accumulators
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc::smem_u32(pair_done + (j & (NPB - 1)))));
+                go += R;
             }
         }
         __syncwarp();
     } else {
         // =============================== epilogue ===============================================================
         const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
-        const int gx = x0 + quad * 32 + lane;
         const float slope = PRELU ? cst[26] : 0.f;
         float lmax = 0.f;
+        int gj = 0, go = 0;
 #pragma unroll 1
-        for (int jo = 0; jo < R / 2; jo++) {
-            const int ya = 2 * jo;                         // output rows ya, ya+1 need input rows up to ya+3 = pair jo+1
-            float2 wfa = make_float2(0.f, 0.f), wfb = wfa;
-            if (EPI == EPI_OUTC && a.dwf_out == nullptr && gx < W) {   // issue the wavefield loads before waiting on the MMAs
-                wfa = reinterpret_cast<const float2*>(a.wf)[img + (size_t)(y0 + ya) * W + gx];
-                wfb = reinterpret_cast<const float2*>(a.wf)[img + (size_t)(y0 + ya + 1) * W + gx];
-            }
-            if (!mbar_wait(pair_done + ((jo + 1) & (NPB - 1)), (uint32_t)((jo + 1) / NPB) & 1u)) { ok = false; break; }
-            asm volatile("tcgen05.fence::after_thread_sync;");
-            uint32_t v[2][16];
-            // rows ya (even) and ya+1 sit in adjacent units: unit(ya+1) = unit(ya) - 1
-            const uint32_t tb = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((15 - ((ya + 1) & 15)) * NC);
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                         : "=r"(v[1][0]), "=r"(v[1][1]), "=r"(v[1][2]), "=r"(v[1][3]), "=r"(v[1][4]), "=r"(v[1][5]), "=r"(v[1][6]), "=r"(v[1][7]),
-                           "=r"(v[1][8]), "=r"(v[1][9]), "=r"(v[1][10]), "=r"(v[1][11]), "=r"(v[1][12]), "=r"(v[1][13]), "=r"(v[1][14]), "=r"(v[1][15])
-                         : "r"(tb));
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                         : "=r"(v[0][0]), "=r"(v[0][1]), "=r"(v[0][2]), "=r"(v[0][3]), "=r"(v[0][4]), "=r"(v[0][5]), "=r"(v[0][6]), "=r"(v[0][7]),
-                           "=r"(v[0][8]), "=r"(v[0][9]), "=r"(v[0][10]), "=r"(v[0][11]), "=r"(v[0][12]), "=r"(v[0][13]), "=r"(v[0][14]), "=r"(v[0][15])
-                         : "r"(tb + NC));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            {
-                const uint32_t z = 0u;   // hand the accumulators back zeroed: the MMAs always accumulate
-                asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(tb), "r"(z));
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            mbar_arrive(tmem_empty + (jo & (NPB - 1)));
-            if (gx < W) {
+        for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
+            const Strip gs = strip_of(st, a);
+            const int gx = gs.x0 + quad * 32 + lane;
+            const int y0 = gs.y0;
+            const size_t img = gs.img;
+#pragma unroll 1
+            for (int jo = 0; jo < gs.R / 2; jo++) {
+                const int ya = 2 * jo;                         // output rows ya, ya+1 need input rows up to ya+3 = pair jo+1
+                float2 wfa = make_float2(0.f, 0.f), wfb = wfa;
+                if (EPI == EPI_OUTC && a.dwf_out == nullptr && gx < W) {   // issue the wavefield loads before waiting on the MMAs
+                    wfa = reinterpret_cast<const float2*>(a.wf)[img + (size_t)(y0 + ya) * W + gx];
+                    wfb = reinterpret_cast<const float2*>(a.wf)[img + (size_t)(y0 + ya + 1) * W + gx];
+                }
+                const int gjd = gj + jo + 1;                   // global input pair that completes these rows
+                if (!mbar_wait(pair_done + (gjd & (NDB - 1)), (uint32_t)(gjd / NDB) & 1u)) { ok = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                uint32_t v[2][16];
+                // rows ya (even) and ya+1 sit in adjacent units: unit(ya+1) = unit(ya) - 1
+                const uint32_t tb = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((15 - ((go + ya + 1) & 15)) * NC);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(v[1][0]), "=r"(v[1][1]), "=r"(v[1][2]), "=r"(v[1][3]), "=r"(v[1][4]), "=r"(v[1][5]), "=r"(v[1][6]), "=r"(v[1][7]),
+                               "=r"(v[1][8]), "=r"(v[1][9]), "=r"(v[1][10]), "=r"(v[1][11]), "=r"(v[1][12]), "=r"(v[1][13]), "=r"(v[1][14]), "=r"(v[1][15])
+                             : "r"(tb));
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(v[0][0]), "=r"(v[0][1]), "=r"(v[0][2]), "=r"(v[0][3]), "=r"(v[0][4]), "=r"(v[0][5]), "=r"(v[0][6]), "=r"(v[0][7]),
+                               "=r"(v[0][8]), "=r"(v[0][9]), "=r"(v[0][10]), "=r"(v[0][11]), "=r"(v[0][12]), "=r"(v[0][13]), "=r"(v[0][14]), "=r"(v[0][15])
+                             : "r"(tb + NC));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                {
+                    const uint32_t z = 0u;   // hand the accumulators back zeroed: the MMAs always accumulate
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(tb), "r"(z));
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                const int gop = (go >> 1) + jo;
+                mbar_arrive(tmem_empty + (gop & (NPB - 1)));
+                if (gx < W) {
 #pragma unroll
-                for (int t = 0; t < 2; t++) {
-                    float o[8];
-#pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        o[c] = fmaf(fmaf(__uint_as_float(v[t][8 + c]), 1.f / 2048.f, __uint_as_float(v[t][c])), out_scale, cst[c]);
-                        if (PRELU) o[c] = o[c] >= 0.f ? o[c] : slope * o[c];
-                    }
-                    const size_t pix = img + (size_t)(y0 + ya + t) * W + gx;
-                    if (EPI == EPI_STORE) {
-#pragma unroll
-                        for (int c = 0; c < 8; c++) lmax = fmaxf(lmax, fabsf(o[c]));
-                        float4* dst = reinterpret_cast<float4*>(a.out + pix * 8);
-                        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-                        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-                    } else {
-                        float o0 = cst[24], o1 = cst[25];
+                    for (int t = 0; t < 2; t++) {
+                        float o[8];
 #pragma unroll
                         for (int c = 0; c < 8; c++) {
-                            o0 = fmaf(o[c], cst[8 + c], o0);
-                            o1 = fmaf(o[c], cst[16 + c], o1);
+                            o[c] = fmaf(fmaf(__uint_as_float(v[t][8 + c]), 1.f / 2048.f, __uint_as_float(v[t][c])), out_scale, cst[c]);
+                            if (PRELU) o[c] = o[c] >= 0.f ? o[c] : slope * o[c];
                         }
-                        if (a.dwf_out != nullptr) {
-                            reinterpret_cast<float2*>(a.dwf_out)[pix] = make_float2(o0, o1);
+                        const size_t pix = img + (size_t)(y0 + ya + t) * W + gx;
+                        if (EPI == EPI_STORE) {
+#pragma unroll
+                            for (int c = 0; c < 8; c++) lmax = fmaxf(lmax, fabsf(o[c]));
+                            float4* dst = reinterpret_cast<float4*>(a.out + pix * 8);
+                            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
                         } else {
-                            const float2 u = t == 0 ? wfa : wfb;
-                            const float2 nw = make_float2(o0 / 1e3f + u.x, o1 / 1e3f + u.y);   // hybridnet.py:570
-                            reinterpret_cast<float2*>(a.wf)[pix] = nw;
-                            lmax = fmaxf(lmax, fmaxf(fabsf(nw.x), fabsf(nw.y)));
+                            float o0 = cst[24], o1 = cst[25];
+#pragma unroll
+                            for (int c = 0; c < 8; c++) {
+                                o0 = fmaf(o[c], cst[8 + c], o0);
+                                o1 = fmaf(o[c], cst[16 + c], o1);
+                            }
+                            if (a.dwf_out != nullptr) {
+                                reinterpret_cast<float2*>(a.dwf_out)[pix] = make_float2(o0, o1);
+                            } else {
+                                const float2 u = t == 0 ? wfa : wfb;
+                                const float2 nw = make_float2(o0 / 1e3f + u.x, o1 / 1e3f + u.y);   // hybridnet.py:570
+                                reinterpret_cast<float2*>(a.wf)[pix] = nw;
+                                lmax = fmaxf(lmax, fmaxf(fabsf(nw.x), fabsf(nw.y)));
+                            }
                         }
                     }
                 }
             }
+            gj += gs.NP;
+            go += gs.R;
         }
         publish_amax(a.amax_out, lmax);
     }

@@ -93,6 +93,7 @@ struct hn_ctx {
     unsigned* amax = nullptr;  // [64] running max |x| per activation tensor (publish_amax), feeds the fp16 block scales
     int tc_min_res = 16;       // use the tensor-core kernels for levels with resolution >= this
     int tcr_min_res = 48;      // row-streaming tensor-core kernel for widths >= this (128-wide strips)
+    int num_sms = 148;
     Weights W;
     // residual norms
     double* ssq = nullptr;
@@ -400,8 +401,11 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
             t.amax_in0 = a.amax_in0; t.amax_in1 = a.amax_in1; t.amax_out = a.amax_out;
             t.error_flag = c->err_flag; t.sigma_max = c->pml > 0 ? (float)c->sigma_max : 0.f; t.w_inv_scale = a.tc_inv;
             t.H = a.H; t.W = a.W;
-            dim3 tgrid((a.W + tcr::CW - 1) / tcr::CW, (a.H + tcr::ROWS - 1) / tcr::ROWS, B);
-            tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI><<<tgrid, dim3(tcr::THREADS), tcr::smem_bytes(SRC), st>>>(t);
+            t.nsx = (a.W + tcr::CW - 1) / tcr::CW;
+            t.nsy = (a.H + tcr::ROWS - 1) / tcr::ROWS;
+            t.total_strips = t.nsx * t.nsy * B;
+            const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;   // persistent: 2 CTAs per SM
+            tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI><<<dim3(tgrid), dim3(tcr::THREADS), tcr::smem_bytes(SRC), st>>>(t);
             c->launches++;
             return HN_OK;
         }
@@ -618,8 +622,12 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     cudaDeviceProp prop;
     HN_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(HN_ERR_CUDA, "libhelmnet_sm100 needs a compute capability 10.x (Blackwell) device");
+    const int num_sms_ = prop.multiProcessorCount;
+#else
+    const int num_sms_ = 148;
 #endif
     hn_ctx* c = new hn_ctx();
+    c->num_sms = num_sms_;
     c->device = device;
     c->n = n;
     c->max_batch = max_batch;
