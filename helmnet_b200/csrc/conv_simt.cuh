@@ -29,7 +29,8 @@ enum ConvSrc : int {
 };
 enum ConvEpi : int {
     EPI_STORE = 0,  // bias (+PReLU) -> NHWC store
-    EPI_OUTC = 1    // bias -> 1x1 outc (8->2) -> wf += out/1e3   (or raw out when dwf_out != nullptr)
+    EPI_OUTC = 1,   // bias -> 1x1 outc (8->2) -> wf += out/1e3   (or raw out when dwf_out != nullptr)
+    EPI_STORE2 = 2  // tcgen05 kernels only: C_out = 2 layer padded to 8 columns, store channels 0,1 as float2
 };
 
 __host__ __device__ constexpr int src_planes(int src) {
@@ -42,6 +43,7 @@ struct Conv3Args {
     const float* sigma;   // SRC_INC: 1-D PML sigma profile [W]
     const float* w;       // packed [planes][9 taps][4 ci][COUT]
     const float* bias;    // [COUT]
+    const float* bias8;   // bias zero-padded to 8 (tcgen05 C_out = 2 path)
     const float* slope;   // PReLU slope (device scalar) when PRELU
     float* out;           // NHWC COUT
     const float* wo;      // EPI_OUTC: outc weight [2][8]

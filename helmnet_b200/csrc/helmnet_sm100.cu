@@ -50,6 +50,7 @@ static int fail(int code, const std::string& msg) {
 
 struct ConvW {      // offsets (in floats) into the packed device blob
     size_t w = 0, b = 0, slope = 0;
+    size_t b8 = 0;            // bias zero-padded to 8 entries (tcgen05 kernels always read 8)
     size_t tc = (size_t)-1;   // offset (in halfs) of the tcgen05 B-operand image, C_out = 8 layers only
     size_t tcr = (size_t)-1;  // same for the row-streaming kernel (N = 48 images)
     float tc_inv = 1.f;       // 2^-kw, inverse of the layer's weight block scale
@@ -311,10 +312,10 @@ static void pack_tc(Packer& pk, const float* w, int cin, ConvW& out) {
 }
 // Row-streaming kernel (conv_tcr.cuh): per (group g, dx) a 48 x 16 fp16 B operand, column n = dy*16 + h*8 + co
 // (h = 0: hi*W_hi part, h = 1: hi*W_lo + lo*W_hi part), same canonical layout, 1536 B each.
-static void pack_tcr(Packer& pk, const float* w, int cin, ConvW& out) {
+static void pack_tcr(Packer& pk, const float* w, int cin, ConvW& out, int cout = 8) {
     const int G = (cin + 7) / 8;
     float mx = 0.f;
-    for (int i = 0; i < 8 * cin * 9; i++) mx = fmaxf(mx, fabsf(w[i]));
+    for (int i = 0; i < cout * cin * 9; i++) mx = fmaxf(mx, fabsf(w[i]));
     int ex = 0;
     if (mx > 0.f) frexpf(mx, &ex);
     const int kw = 10 - ex;
@@ -327,7 +328,7 @@ static void pack_tcr(Packer& pk, const float* w, int cin, ConvW& out) {
             for (int n = 0; n < 48; n++)
                 for (int k = 0; k < 16; k++) {
                     const int dy = n / 16, h = (n / 8) & 1, co = n & 7, ci = g * 8 + (k & 7);
-                    const float wv = ci < cin ? w[(co * cin + ci) * 9 + dy * 3 + dx] * scale : 0.f;
+                    const float wv = (ci < cin && co < cout) ? w[(co * cin + ci) * 9 + dy * 3 + dx] * scale : 0.f;
                     const __half hi = __float2half_rn(wv);
                     const __half lo = __float2half_rn((wv - __half2float(hi)) * 2048.f);
                     __half val = __float2half_rn(0.f);
@@ -362,12 +363,18 @@ static void pack_double_conv(Packer& pk, Cursor& cur, ConvW out[2], int cin, int
     if (!cur.ok) return;
     out[0].w = pack_conv3(pk, w0, cmid, cin);
     out[0].b = pack_vec(pk, b0, cmid);
+    {
+        float b8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < cmid && i < 8; i++) b8[i] = b0[i];
+        out[0].b8 = pack_vec(pk, b8, 8);
+    }
     out[0].slope = pack_vec(pk, sl, 1);
     out[1].w = pack_conv3(pk, w1, cout, cmid);
     out[1].b = pack_vec(pk, b1, cout);
     out[1].slope = out[0].slope;
 #ifdef HN_HAVE_TC
     if (cmid == 8) { pack_tc(pk, w0, cin, out[0]); pack_tcr(pk, w0, cin, out[0]); }
+    if (cmid == 2 && cin == 10) pack_tcr(pk, w0, cin, out[0], 2);   // conv_state.0: C_out = 2 padded to 8 accumulator columns
     if (cout == 8 && cmid == 8) { pack_tc(pk, w1, cmid, out[1]); pack_tcr(pk, w1, cmid, out[1]); }
 #endif
 }
@@ -386,6 +393,30 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
     }
 #endif
 #ifdef HN_HAVE_TC
+    if constexpr (COUT == 2 && SRC == SRC_A8_B2 && EPI == EPI_STORE) {
+        if (c->engine == 1 && a.tcr_bmat != nullptr && a.W >= c->tcr_min_res && (a.H % 2) == 0 && a.amax_in0 != nullptr) {
+            static bool tcr2_attr_done[16] = {false};
+            if (!tcr2_attr_done[c->device & 15]) {
+                HN_CUDA(cudaFuncSetAttribute(tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI_STORE2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)tcr::smem_bytes(SRC)));
+                tcr2_attr_done[c->device & 15] = true;
+            }
+            tcr::Args t;
+            t.inA = a.inA; t.inB = a.inB; t.sigma = a.sigma;
+            t.bmat = reinterpret_cast<const __half*>(a.tcr_bmat);
+            t.bias = a.bias8; t.slope = a.slope; t.out = a.out; t.wo = nullptr; t.bo = nullptr; t.wf = nullptr; t.dwf_out = nullptr;
+            t.amax_in0 = a.amax_in0; t.amax_in1 = a.amax_in1; t.amax_out = a.amax_out;
+            t.error_flag = c->err_flag; t.sigma_max = 0.f; t.w_inv_scale = a.tc_inv;
+            t.H = a.H; t.W = a.W;
+            t.nsx = (a.W + tcr::CW - 1) / tcr::CW;
+            t.nsy = (a.H + tcr::ROWS - 1) / tcr::ROWS;
+            t.total_strips = t.nsx * t.nsy * B;
+            const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;
+            tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI_STORE2><<<dim3(tgrid), dim3(tcr::THREADS), tcr::smem_bytes(SRC), st>>>(t);
+            c->launches++;
+            return HN_OK;
+        }
+    }
     if constexpr (COUT == 8) {
         if (c->engine == 1 && a.tcr_bmat != nullptr && a.W >= c->tcr_min_res && (a.H % 2) == 0 && a.amax_in0 != nullptr) {
             static bool tcr_attr_done[16] = {false};
@@ -447,6 +478,7 @@ static Conv3Args conv_args(hn_ctx* c, const ConvW& w, const float* inA, const fl
     a.sigma = c->sigma1d;
     a.w = c->wdev + w.w;
     a.bias = c->wdev + w.b;
+    a.bias8 = c->wdev + w.b8;
     a.slope = c->wdev + w.slope;
     a.out = out;
     a.H = r;
@@ -501,7 +533,7 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
         HN_TRY((launch_conv3<SRC_A8_B2, 8, true, EPI_STORE>(c, s0, B, st)));
         Conv3Args s1 = conv_args(c, W.sig[d][1], c->mid[d], nullptr, c->skip[d], r, S_SKIP + d, S_MID + d);
         HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, s1, B, st)));
-        Conv3Args t0 = conv_args(c, W.sta[d][0], c->skip[d], c->state[d][cur], c->mid2[d], r);
+        Conv3Args t0 = conv_args(c, W.sta[d][0], c->skip[d], c->state[d][cur], c->mid2[d], r, -1, S_SKIP + d, S_STATE + 2 * d + cur);
         HN_TRY((launch_conv3<SRC_A8_B2, 2, true, EPI_STORE>(c, t0, B, st)));
         Conv3Args t1 = conv_args(c, W.sta[d][1], c->mid2[d], nullptr, c->state[d][nxt], r, S_STATE + 2 * d + nxt);
         HN_TRY((launch_conv3<SRC_A2, 2, false, EPI_STORE>(c, t1, B, st)));
