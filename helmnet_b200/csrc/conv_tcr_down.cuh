@@ -1,0 +1,322 @@
+// conv_tcr_down.cuh -- the encoder's down-sampling Conv2d(8, 8, kernel 8, stride 2, padding 3)
+// (helmnet/architectures.py:209-211) as a row-streaming tcgen05 implicit GEMM; same machinery as conv_tcr.cuh.
+//
+//   out[oy][ox][co] = b[co] + sum_{ky,kx,ci} in[2 oy - 3 + ky][2 ox - 3 + kx][ci] * W[co][ci][ky][kx]
+//
+// GEMM mapping: M = 128 consecutive output columns ox.  For a fixed kx the inputs 2 ox - 3 + kx of consecutive ox
+// are two pixels apart, so each staged input row is stored de-interleaved by x parity: plane[par][h] holds pixel
+// xb + 2 h + par (xb = 2 ox0 - 4) and "A row ox, tap kx" is plane[(kx+1)&1][ox + (kx+1)/2] -- again a pure
+// start-address shift of a K-major SWIZZLE_NONE operand.  Input row k = 2 j + t of a strip feeds the four output
+// rows j, j-1, j-2, j-3 through ky = 2 m + t (m = 0..3), so the ky taps go into N: one MMA per (row, kx) with
+// N = 4 x (8 + 8) = 64 accumulator columns that land on the adjacent 16-column accumulators of those four output
+// rows (output-stationary ring of 16 units in 256 TMEM columns, zeroed by the epilogue, accumulate always on).
+// 16 MMAs (N = 64, ~48 cycles each) per 128 output pixels instead of 64 MMAs in a tap-per-MMA mapping.
+//
+// Roles, rings and the persistent strip walk are those of conv_tcr.cuh: TMA warp -> fp32 staging ring,
+// 2 converter teams (one input row each) -> fp16 hi/lo operand ring, one MMA-issuing thread, 4 epilogue warps.
+#pragma once
+#include "conv_tcr.cuh"
+
+namespace hn {
+namespace tcd {
+
+using tcr::CW;
+using tcr::PS;
+using tcr::TEAM;
+using tcr::PROD_WARPS;
+using tcr::EPI_WARPS;
+using tcr::MMA_WARP;
+using tcr::TMA_WARP;
+using tcr::THREADS;
+using tcr::TMEM_COLS;
+using tcr::mbar_wait;
+using tcr::mbar_arrive;
+using tcr::mbar_arrive_expect_tx;
+using tcr::tma_load_1d;
+
+constexpr int ROWS_O = 32;                 // output rows per strip
+constexpr int NC = 16;                     // accumulator columns per output row
+constexpr int SRP = 2;                     // operand ring depth (input row pairs)
+constexpr int NSP = 2;                     // staging ring depth (input row pairs)
+constexpr int NUB = 16;                    // one barrier per accumulator unit (output row)
+constexpr int NDB = 32;                    // input-pair completion barriers
+constexpr int ROW_OP_BYTES = 4 * PS * 16;  // one operand row: [par 0: hi, lo][par 1: hi, lo] x PS entries
+constexpr int ROW_ST_BYTES = 2 * PS * 32;  // one staged fp32 row: 2*PS pixels x 32 B (264 used)
+constexpr int BIMG_BYTES = 2048;           // one (t, kx) B operand: 64 x 16 fp16
+constexpr size_t SMEM_BYTES = (size_t)NSP * 2 * ROW_ST_BYTES + (size_t)SRP * 2 * ROW_OP_BYTES + 16 * BIMG_BYTES + 768;
+
+struct Args {
+    const float* in;            // NHWC8 [B][H][W]
+    const __half* bmat;         // [2 t][8 kx] x 2048 B canonical K-major images (host packed)
+    const float* bias;          // [8]
+    float* out;                 // NHWC8 [B][H/2][W/2]
+    const unsigned* amax_in;
+    unsigned* amax_out;
+    int* error_flag;
+    float w_inv_scale;
+    int H, W;                   // input resolution
+    int nsx, nsy, total_strips;
+};
+
+struct Strip {
+    int ox0, oy0, Ro, NP;
+    size_t img_in, img_out;
+};
+__device__ __forceinline__ Strip strip_of(int st, const Args& a) {
+    Strip g;
+    const int sx = st % a.nsx, r = st / a.nsx;
+    const int sy = r % a.nsy, b = r / a.nsy;
+    g.ox0 = sx * CW;
+    g.oy0 = sy * ROWS_O;
+    g.Ro = min(ROWS_O, (a.H >> 1) - g.oy0);
+    g.NP = g.Ro + 3;            // input row pairs: rows k = 0 .. 2 Ro + 5, image row 2 oy0 - 3 + k
+    g.img_in = (size_t)b * a.H * a.W;
+    g.img_out = (size_t)b * (a.H >> 1) * (a.W >> 1);
+    return g;
+}
+
+__global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
+    constexpr uint32_t kIdescBase = (1u << 4) | ((128u >> 4) << 24);
+    extern __shared__ __align__(128) uint8_t smem_tcd[];
+    uint8_t* stage = smem_tcd;                                          // [NSP][2] fp32 rows
+    uint8_t* ring = stage + (size_t)NSP * 2 * ROW_ST_BYTES;             // [SRP][2] operand rows
+    uint8_t* bsm = ring + (size_t)SRP * 2 * ROW_OP_BYTES;               // [2][8] B images
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + 16 * BIMG_BYTES);
+    uint64_t* smem_full = bars;                  // [SRP]  2 x 136 converter arrivals
+    uint64_t* pair_done = smem_full + SRP;       // [NDB]  tcgen05.commit
+    uint64_t* tmem_empty = pair_done + NDB;      // [NUB]  128 epilogue arrivals per output row
+    uint64_t* stage_full = tmem_empty + NUB;     // [NSP]
+    uint64_t* stage_empty = stage_full + NSP;    // [NSP]  2 x 136
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_empty + NSP);
+    float* cst = reinterpret_cast<float*>(tmem_slot + 4);   // bias[8]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int H = a.H, W = a.W, Wo = W >> 1;
+
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < SRP; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(smem_full + i)), "r"(2 * PS));
+        for (int i = 0; i < NDB; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(pair_done + i)));
+        for (int i = 0; i < NUB; i++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(tmem_empty + i)), "r"(EPI_WARPS * 32));
+        for (int i = 0; i < NSP; i++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(stage_full + i)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(stage_empty + i)), "r"(2 * PS));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    {
+        const uint4* bg = reinterpret_cast<const uint4*>(a.bmat);
+        uint4* bs = reinterpret_cast<uint4*>(bsm);
+        for (int i = tid; i < 16 * BIMG_BYTES / 16; i += THREADS) bs[i] = __ldg(bg + i);
+        if (tid < 8) cst[tid] = __ldg(a.bias + tid);
+    }
+    asm volatile("fence.proxy.async.shared::cta;");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp > MMA_WARP && warp < TMA_WARP) {
+        const uint32_t z = 0u;
+#pragma unroll 1
+        for (int u = 0; u < 16; u++) {
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(u * NC);
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z));
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+
+    const float amax = __uint_as_float(__ldg(a.amax_in));
+    int e = (int)((__float_as_uint(amax) >> 23) & 0xffu);
+    if (e < 40 || e > 250) e = 127;
+    const float mult = __uint_as_float((uint32_t)(267 - e) << 23);
+    const float out_scale = __uint_as_float((uint32_t)(e - 13) << 23) * a.w_inv_scale;
+
+    bool ok = true;
+    if (warp == TMA_WARP) {
+        // =============================== TMA issuer ===============================================================
+        if (lane == 0) {
+            int gj = 0;
+#pragma unroll 1
+            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
+                const Strip g = strip_of(st, a);
+                const int xb = 2 * g.ox0 - 4;                               // first staged pixel (even)
+                const int lo = max(0, xb), hi = min(W, xb + 2 * PS - 8);    // 264 pixels cover every tap of 128 outputs
+                const uint32_t rb = (uint32_t)(hi - lo) * 32u;
+#pragma unroll 1
+                for (int j = 0; j < g.NP; j++, gj++) {
+                    const int sidx = gj % NSP;
+                    if (!mbar_wait(stage_empty + sidx, ((uint32_t)(gj / NSP) & 1u) ^ 1u)) { ok = false; break; }
+                    const int gy0 = 2 * g.oy0 - 3 + 2 * j;
+                    const bool v0 = gy0 >= 0 && gy0 < H, v1 = gy0 + 1 >= 0 && gy0 + 1 < H;
+                    if (!v0 && !v1) {
+                        mbar_arrive(stage_full + sidx);
+                        continue;
+                    }
+                    mbar_arrive_expect_tx(stage_full + sidx, ((uint32_t)v0 + (uint32_t)v1) * rb);
+#pragma unroll
+                    for (int t = 0; t < 2; t++) {
+                        if (!(t == 0 ? v0 : v1)) continue;
+                        uint8_t* dst = stage + (size_t)(sidx * 2 + t) * ROW_ST_BYTES;
+                        tma_load_1d(dst + (lo - xb) * 32, a.in + (g.img_in + (size_t)(gy0 + t) * W + lo) * 8, rb, stage_full + sidx);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp < PROD_WARPS) {
+        // =============================== converters ===============================================================
+        const int team = tid / TEAM, p = tid - team * TEAM;     // p: half-position h; handles pixels xb + 2p and xb + 2p + 1
+        if (p < PS) {
+            int gj = 0;
+#pragma unroll 1
+            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
+                const Strip g = strip_of(st, a);
+                const int xb = 2 * g.ox0 - 4;
+                const int gxe = xb + 2 * p, gxo = gxe + 1;
+                const bool oke = (p < PS - 4) && gxe >= 0 && gxe < W, oko = (p < PS - 4) && gxo >= 0 && gxo < W;
+#pragma unroll 1
+                for (int j = 0; j < g.NP; j++, gj++) {
+                    const int sidx = gj % NSP, s = gj % SRP;
+                    const int gy = 2 * g.oy0 - 3 + 2 * j + team;
+                    float ge[8], go_[8];
+#pragma unroll
+                    for (int c = 0; c < 8; c++) { ge[c] = 0.f; go_[c] = 0.f; }
+                    if (!mbar_wait(stage_full + sidx, (uint32_t)(gj / NSP) & 1u)) { ok = false; break; }
+                    if (gy >= 0 && gy < H) {
+                        const uint8_t* src = stage + (size_t)(sidx * 2 + team) * ROW_ST_BYTES + (size_t)p * 64;
+                        if (oke) {
+                            const float4 q0 = *reinterpret_cast<const float4*>(src), q1 = *reinterpret_cast<const float4*>(src + 16);
+                            ge[0] = q0.x; ge[1] = q0.y; ge[2] = q0.z; ge[3] = q0.w; ge[4] = q1.x; ge[5] = q1.y; ge[6] = q1.z; ge[7] = q1.w;
+                        }
+                        if (oko) {
+                            const float4 q0 = *reinterpret_cast<const float4*>(src + 32), q1 = *reinterpret_cast<const float4*>(src + 48);
+                            go_[0] = q0.x; go_[1] = q0.y; go_[2] = q0.z; go_[3] = q0.w; go_[4] = q1.x; go_[5] = q1.y; go_[6] = q1.z; go_[7] = q1.w;
+                        }
+                    }
+                    if (gj >= SRP && !mbar_wait(pair_done + ((gj - SRP) & (NDB - 1)), (uint32_t)((gj - SRP) / NDB) & 1u)) { ok = false; break; }
+                    uint4* slot = reinterpret_cast<uint4*>(ring + (size_t)(s * 2 + team) * ROW_OP_BYTES);
+                    uint4 hi4, lo4;
+                    tc::split8(ge, mult, hi4, lo4);
+                    slot[p] = hi4;
+                    slot[PS + p] = lo4;
+                    tc::split8(go_, mult, hi4, lo4);
+                    slot[2 * PS + p] = hi4;
+                    slot[3 * PS + p] = lo4;
+                    asm volatile("fence.proxy.async.shared::cta;");
+                    mbar_arrive(smem_full + s);
+                    mbar_arrive(stage_empty + sidx);
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // =============================== MMA issuer ===============================================================
+        if (lane == 0) {
+            const uint32_t ring_base = tc::smem_u32(ring), b_base = tc::smem_u32(bsm);
+            // per-kx A descriptor of operand row 0: parity plane (kx+1)&1, start shift (kx+1)>>1 entries
+            uint64_t da0[8];
+#pragma unroll
+            for (int kx = 0; kx < 8; kx++)
+                da0[kx] = tc::smem_desc(ring_base + (uint32_t)(((kx + 1) & 1) * 2 * PS * 16 + ((kx + 1) >> 1) * 16), PS * 16, 128);
+            const uint64_t db0 = tc::smem_desc(b_base, 128, 256);
+            constexpr uint32_t kRow16 = ROW_OP_BYTES >> 4;
+            constexpr uint32_t kIdesc64 = kIdescBase | (8u << 17);
+            int gj = 0, go = 0;
+#pragma unroll 1
+            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
+                const Strip gs = strip_of(st, a);
+                const int Ro = gs.Ro;
+#pragma unroll 1
+                for (int j = 0; j < gs.NP; j++, gj++) {
+                    const int s = gj % SRP;
+                    if (!mbar_wait(smem_full + s, (uint32_t)(gj / SRP) & 1u)) { ok = false; break; }
+                    const int gr = go + j;                    // global index of output row j (first touched by this pair)
+                    if (j < Ro && !mbar_wait(tmem_empty + (gr & (NUB - 1)), ((uint32_t)(gr / NUB) & 1u) ^ 1u)) { ok = false; break; }
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    // live output rows of this pair: j - m, m in [mlo, mhi]
+                    const int mlo = max(0, j - (Ro - 1)), mhi = min(3, j);
+                    int m = mlo;
+                    while (m <= mhi) {
+                        const int u = 15 - ((gr - m) & 15);
+                        int len = 1;
+                        while (m + len <= mhi && u + len <= 15) len++;
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(u * NC);
+                        const uint32_t idesc = (len == 4) ? kIdesc64 : (kIdescBase | ((uint32_t)(2 * len) << 17));
+#pragma unroll
+                        for (int t = 0; t < 2; t++) {
+                            const uint64_t soff = (uint64_t)((uint32_t)(s * 2 + t) * kRow16);
+#pragma unroll
+                            for (int kx = 0; kx < 8; kx++)
+                                asm volatile(
+                                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                                    "l"(da0[kx] + soff), "l"(db0 + (uint64_t)((t * 8 + kx) * (BIMG_BYTES >> 4) + m * 32)), "r"(idesc), "r"(1u));
+                        }
+                        m += len;
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc::smem_u32(pair_done + (gj & (NDB - 1)))));
+                }
+                go += Ro;
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================== epilogue ===============================================================
+        const int quad = warp & 3;
+        float lmax = 0.f;
+        int gj = 0, go = 0;
+#pragma unroll 1
+        for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
+            const Strip gs = strip_of(st, a);
+            const int ox = gs.ox0 + quad * 32 + lane;
+#pragma unroll 1
+            for (int oyl = 0; oyl < gs.Ro; oyl++) {
+                const int gjd = gj + oyl + 3;                  // input pair that completes output row oyl
+                if (!mbar_wait(pair_done + (gjd & (NDB - 1)), (uint32_t)(gjd / NDB) & 1u)) { ok = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const int gr = go + oyl;
+                uint32_t v[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((15 - (gr & 15)) * NC);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                               "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                {
+                    const uint32_t z = 0u;
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z));
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                mbar_arrive(tmem_empty + (gr & (NUB - 1)));
+                if (ox < Wo) {
+                    float o[8];
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        o[c] = fmaf(fmaf(__uint_as_float(v[8 + c]), 1.f / 2048.f, __uint_as_float(v[c])), out_scale, cst[c]);
+                        lmax = fmaxf(lmax, fabsf(o[c]));
+                    }
+                    float4* dst = reinterpret_cast<float4*>(a.out + (gs.img_out + (size_t)(gs.oy0 + oyl) * Wo + ox) * 8);
+                    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+                }
+            }
+            gj += gs.NP;
+            go += gs.Ro;
+        }
+        publish_amax(a.amax_out, lmax);
+    }
+    if (!ok) *a.error_flag = 1;
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+}
+
+}  // namespace tcd
+}  // namespace hn

@@ -24,6 +24,7 @@
 #ifndef HN_EMU
 #include "conv_tc.cuh"
 #include "conv_tcr.cuh"
+#include "conv_tcr_down.cuh"
 #define HN_HAVE_TC 1
 #endif
 
@@ -95,6 +96,7 @@ struct hn_ctx {
     int tc_min_res = 16;       // use the tensor-core kernels for levels with resolution >= this
     int tcr_min_res = 48;      // row-streaming tensor-core kernel for widths >= this (128-wide strips)
     int num_sms = 148;
+    int tcd_min_res = 64;      // tensor-core down-sampling for output widths >= this
     Weights W;
     // residual norms
     double* ssq = nullptr;
@@ -340,6 +342,35 @@ static void pack_tcr(Packer& pk, const float* w, int cin, ConvW& out, int cout =
                     pk.halfs[out.tcr + (size_t)(g * 3 + dx) * 768 + byte / 2] = bits;
                 }
 }
+// Down-sampling conv on tensor cores (conv_tcr_down.cuh): W[co][ci][8][8] -> per (t = ky parity, kx) a 64 x 16 fp16
+// B operand, column n = m*16 + h*8 + co with ky = 2m + t.
+static void pack_tcd(Packer& pk, const float* w, ConvW& out) {
+    float mx = 0.f;
+    for (int i = 0; i < 8 * 8 * 64; i++) mx = fmaxf(mx, fabsf(w[i]));
+    int ex = 0;
+    if (mx > 0.f) frexpf(mx, &ex);
+    const int kw = 10 - ex;
+    const float scale = ldexpf(1.f, kw);
+    out.tc_inv = ldexpf(1.f, -kw);
+    out.tcr = pk.halfs.size();
+    pk.halfs.resize(out.tcr + (size_t)16 * 1024, 0);
+    for (int t = 0; t < 2; t++)
+        for (int kx = 0; kx < 8; kx++)
+            for (int n = 0; n < 64; n++)
+                for (int k = 0; k < 16; k++) {
+                    const int m = n / 16, h = (n / 8) & 1, co = n & 7, ci = k & 7, ky = 2 * m + t;
+                    const float wv = w[((co * 8 + ci) * 8 + ky) * 8 + kx] * scale;
+                    const __half hi = __float2half_rn(wv);
+                    const __half lo = __float2half_rn((wv - __half2float(hi)) * 2048.f);
+                    __half val = __float2half_rn(0.f);
+                    if (h == 0) { if (k < 8) val = hi; }
+                    else val = (k < 8) ? lo : hi;
+                    const int byte = (n / 8) * 256 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2;
+                    uint16_t bits;
+                    memcpy(&bits, &val, 2);
+                    pk.halfs[out.tcr + (size_t)(t * 8 + kx) * 1024 + byte / 2] = bits;
+                }
+}
 #endif
 
 struct Cursor {
@@ -545,6 +576,33 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
         dn.amax_out = c->amax + S_X + d + 1;
         dn.H = r;
         dn.W = r;
+#ifdef HN_HAVE_TC
+        if (c->engine == 1 && W.down[d].tcr != (size_t)-1 && r / 2 >= c->tcd_min_res) {
+            static bool tcd_attr_done[16] = {false};
+            if (!tcd_attr_done[c->device & 15]) {
+                HN_CUDA(cudaFuncSetAttribute(tcd::down_tcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcd::SMEM_BYTES));
+                tcd_attr_done[c->device & 15] = true;
+            }
+            tcd::Args t;
+            t.in = c->skip[d];
+            t.bmat = reinterpret_cast<const __half*>(c->tcw + W.down[d].tcr);
+            t.bias = c->wdev + W.down[d].b;
+            t.out = c->x[d + 1];
+            t.amax_in = c->amax + S_SKIP + d;
+            t.amax_out = c->amax + S_X + d + 1;
+            t.error_flag = c->err_flag;
+            t.w_inv_scale = W.down[d].tc_inv;
+            t.H = r;
+            t.W = r;
+            t.nsx = (r / 2 + tcr::CW - 1) / tcr::CW;
+            t.nsy = (r / 2 + tcd::ROWS_O - 1) / tcd::ROWS_O;
+            t.total_strips = t.nsx * t.nsy * B;
+            const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;
+            tcd::down_tcr_kernel<<<dim3(tgrid), dim3(tcr::THREADS), tcd::SMEM_BYTES, st>>>(t);
+            c->launches++;
+            continue;
+        }
+#endif
         dim3 g((r / 2 + DN_TX - 1) / DN_TX, (r / 2 + DN_TY - 1) / DN_TY, B);
         HN_LAUNCH(down_kernel, g, dim3(DN_THREADS), DN_SMEM, st, dn);
         c->launches++;
@@ -713,7 +771,7 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     A_(c->ssq1, B);
     A_(c->iter_dev, 4);
     A_(c->wdev, 65536);
-    A_(c->tcw, 163840);
+    A_(c->tcw, 327680);
     A_(c->err_flag, 4);
     A_(c->amax, 64);
 #undef A_
@@ -721,6 +779,7 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     if (cudaMemset(c->err_flag, 0, 16) != cudaSuccess) return cleanup(fail(HN_ERR_CUDA, "cudaMemset failed"));
     if (const char* mr = getenv("HELMNET_TC_MIN_RES")) c->tc_min_res = atoi(mr);
     if (const char* mr = getenv("HELMNET_TCR_MIN_RES")) c->tcr_min_res = atoi(mr);
+    if (const char* mr = getenv("HELMNET_TCD_MIN_RES")) c->tcd_min_res = atoi(mr);
     if (const char* en = getenv("HELMNET_ENGINE")) c->engine = atoi(en) == 1 ? 1 : 0;
 #ifdef HN_EMU
     c->engine = 0;
@@ -765,6 +824,9 @@ int hn_load_weights(hn_ctx* c, const float* host_blob, size_t n_floats) {
         if (cur.ok) {
             W.down[d].w = pack_down(pk, dw);
             W.down[d].b = pack_vec(pk, db, 8);
+#ifdef HN_HAVE_TC
+            pack_tcd(pk, dw, W.down[d]);
+#endif
         }
         pack_double_conv(pk, cur, W.sta[d], 10, 2, 2);
     }
@@ -793,7 +855,7 @@ int hn_load_weights(hn_ctx* c, const float* host_blob, size_t n_floats) {
     HN_CUDA(cudaDeviceSynchronize());
 #endif
     HN_CUDA(cudaMemcpy(c->wdev, pk.blob.data(), pk.blob.size() * 4, cudaMemcpyHostToDevice));
-    if (pk.halfs.size() > 163840) return fail(HN_ERR_STATE, "tensor-core weight images exceed the reserved buffer");
+    if (pk.halfs.size() > 327680) return fail(HN_ERR_STATE, "tensor-core weight images exceed the reserved buffer");
     if (!pk.halfs.empty()) HN_CUDA(cudaMemcpy(c->tcw, pk.halfs.data(), pk.halfs.size() * 2, cudaMemcpyHostToDevice));
     c->weights_set = true;
     return HN_OK;
