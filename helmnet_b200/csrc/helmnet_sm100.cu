@@ -25,6 +25,7 @@
 #include "conv_tc.cuh"
 #include "conv_tcr.cuh"
 #include "conv_tcr_down.cuh"
+#include "conv_tcr_up.cuh"
 #define HN_HAVE_TC 1
 #endif
 
@@ -371,6 +372,35 @@ static void pack_tcd(Packer& pk, const float* w, ConvW& out) {
                     pk.halfs[out.tcr + (size_t)(t * 8 + kx) * 1024 + byte / 2] = bits;
                 }
 }
+// Up-sampling transposed conv on tensor cores (conv_tcr_up.cuh): W[ci][co][8][8] -> per shift s = si - 2 a 256 x 16
+// fp16 B operand, column n = ky*32 + px*16 + h*8 + co with kx = px + 3 - 2 s (zero block when kx is out of range).
+static void pack_tcu(Packer& pk, const float* w, ConvW& out) {
+    float mx = 0.f;
+    for (int i = 0; i < 8 * 8 * 64; i++) mx = fmaxf(mx, fabsf(w[i]));
+    int ex = 0;
+    if (mx > 0.f) frexpf(mx, &ex);
+    const int kw = 10 - ex;
+    const float scale = ldexpf(1.f, kw);
+    out.tc_inv = ldexpf(1.f, -kw);
+    out.tcr = pk.halfs.size();
+    pk.halfs.resize(out.tcr + (size_t)5 * 4096, 0);
+    for (int si = 0; si < 5; si++)
+        for (int n = 0; n < 256; n++)
+            for (int k = 0; k < 16; k++) {
+                const int ky = n / 32, px = (n / 16) & 1, h = (n / 8) & 1, co = n & 7, ci = k & 7;
+                const int kx = px + 3 - 2 * (si - 2);
+                const float wv = (kx >= 0 && kx < 8) ? w[((ci * 8 + co) * 8 + ky) * 8 + kx] * scale : 0.f;
+                const __half hi = __float2half_rn(wv);
+                const __half lo = __float2half_rn((wv - __half2float(hi)) * 2048.f);
+                __half val = __float2half_rn(0.f);
+                if (h == 0) { if (k < 8) val = hi; }
+                else val = (k < 8) ? lo : hi;
+                const int byte = (n / 8) * 256 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2;
+                uint16_t bits;
+                memcpy(&bits, &val, 2);
+                pk.halfs[out.tcr + (size_t)si * 4096 + byte / 2] = bits;
+            }
+}
 #endif
 
 struct Cursor {
@@ -626,9 +656,37 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
         up.amax_out = c->amax + S_UPO + d;
         up.Hi = r / 2;
         up.Wi = r / 2;
-        dim3 g((r / 2 + UP_TL - 1) / UP_TL, (r / 2 + UP_TL - 1) / UP_TL, B);
-        HN_LAUNCH(up_kernel, g, dim3(UP_THREADS), UP_SMEM, st, up);
-        c->launches++;
+#ifdef HN_HAVE_TC
+        if (c->engine == 1 && W.up[d].tcr != (size_t)-1 && r / 2 >= c->tcd_min_res && ((r / 2) % 2) == 0) {
+            static bool tcu_attr_done[16] = {false};
+            if (!tcu_attr_done[c->device & 15]) {
+                HN_CUDA(cudaFuncSetAttribute(tcu::up_tcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcu::SMEM_BYTES));
+                tcu_attr_done[c->device & 15] = true;
+            }
+            tcu::Args t;
+            t.in = up.in;
+            t.bmat = reinterpret_cast<const __half*>(c->tcw + W.up[d].tcr);
+            t.bias = up.bias;
+            t.out = up.out;
+            t.amax_in = c->amax + ((d == kDepth - 1) ? S_BOT : S_DEC + d + 1);
+            t.amax_out = up.amax_out;
+            t.error_flag = c->err_flag;
+            t.w_inv_scale = W.up[d].tc_inv;
+            t.Hi = r / 2;
+            t.Wi = r / 2;
+            t.nsx = (r / 2 + tcr::CW - 1) / tcr::CW;
+            t.nsy = (r / 2 + tcu::ROWS_I - 1) / tcu::ROWS_I;
+            t.total_strips = t.nsx * t.nsy * B;
+            const int tgrid = t.total_strips < c->num_sms ? t.total_strips : c->num_sms;   // one CTA per SM (owns all 512 TMEM columns)
+            tcu::up_tcr_kernel<<<dim3(tgrid), dim3(tcr::THREADS), tcu::SMEM_BYTES, st>>>(t);
+            c->launches++;
+        } else
+#endif
+        {
+            dim3 g((r / 2 + UP_TL - 1) / UP_TL, (r / 2 + UP_TL - 1) / UP_TL, B);
+            HN_LAUNCH(up_kernel, g, dim3(UP_THREADS), UP_SMEM, st, up);
+            c->launches++;
+        }
         // mid[d] is reused as scratch by inc / encoder / decoder; each use has its own amax slot
         Conv3Args d0 = conv_args(c, W.dec[d][0], c->upo[d], c->skip[d], c->mid[d], r, S_DMID + d, S_UPO + d, S_SKIP + d);
         HN_TRY((launch_conv3<SRC_A8_B8, 8, true, EPI_STORE>(c, d0, B, st)));
@@ -771,7 +829,7 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     A_(c->ssq1, B);
     A_(c->iter_dev, 4);
     A_(c->wdev, 65536);
-    A_(c->tcw, 327680);
+    A_(c->tcw, 458752);
     A_(c->err_flag, 4);
     A_(c->amax, 64);
 #undef A_
@@ -838,6 +896,9 @@ int hn_load_weights(hn_ctx* c, const float* host_blob, size_t n_floats) {
         if (cur.ok) {
             W.up[d].w = pack_up(pk, uw);
             W.up[d].b = pack_vec(pk, ub, 8);
+#ifdef HN_HAVE_TC
+            pack_tcu(pk, uw, W.up[d]);
+#endif
         }
     }
     {
@@ -855,7 +916,7 @@ int hn_load_weights(hn_ctx* c, const float* host_blob, size_t n_floats) {
     HN_CUDA(cudaDeviceSynchronize());
 #endif
     HN_CUDA(cudaMemcpy(c->wdev, pk.blob.data(), pk.blob.size() * 4, cudaMemcpyHostToDevice));
-    if (pk.halfs.size() > 327680) return fail(HN_ERR_STATE, "tensor-core weight images exceed the reserved buffer");
+    if (pk.halfs.size() > 458752) return fail(HN_ERR_STATE, "tensor-core weight images exceed the reserved buffer");
     if (!pk.halfs.empty()) HN_CUDA(cudaMemcpy(c->tcw, pk.halfs.data(), pk.halfs.size() * 2, cudaMemcpyHostToDevice));
     c->weights_set = true;
     return HN_OK;
