@@ -141,6 +141,7 @@ static inline int grid1d(size_t total) {
 // ------------------------------------------------------------------------------------------------
 static void factorize(int n, int* radix, int* nst) {
     int k = 0;
+    while (n % 16 == 0) { radix[k++] = 16; n /= 16; }
     while (n % 4 == 0) { radix[k++] = 4; n /= 4; }
     while (n % 2 == 0) { radix[k++] = 2; n /= 2; }
     for (int p = 3; n > 1; p += 2)
@@ -212,7 +213,7 @@ static int build_tables(hn_ctx* c) {
     c->spec.pml = pml;
     factorize(n, c->spec.radix, &c->spec.nstages);
     // lines per CTA: ~48 KB of line buffers for the row pass; the column pass needs >= 32 B segments
-    int L = 2048 / n;
+    int L = 4096 / n;     // ~100 KB of line buffers: two CTAs per SM
     if (L < 1) L = 1;
     if (L > 16) L = 16;
     c->rows_L = L;

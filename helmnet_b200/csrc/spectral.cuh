@@ -35,9 +35,43 @@ struct SpecTables {
     int radix[kMaxStages];
 };
 
-// Forward FFT of `nl` lines of length n stored with pitch lp in x; y is scratch of the same shape.
-// Stockham autosort, decimation in frequency:  for stage length len = r*m and stride s,
+// Line buffers are padded by one element every 16 (physical index = i + i/16) so that the stride-16 accesses of the
+// radix-16 passes fall on distinct banks.
+__host__ __device__ __forceinline__ int pidx(int i) { return i + (i >> 4); }
+__host__ __device__ inline int line_pitch(int n) { return n + (n >> 4) + 1; }
+
+// 16-point DFT in registers (4 x 4 Cooley-Tukey), natural-order in and out: a[j] <- sum_k a[k] w16^{jk}
+__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+    const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
+    a0 = cadd(t0, t2);
+    a2 = csub(t0, t2);
+    a1 = make_float2(t1.x + t3.y, t1.y - t3.x);   // t1 - i t3
+    a3 = make_float2(t1.x - t3.y, t1.y + t3.x);   // t1 + i t3
+}
+__device__ __forceinline__ void dft16(float2 (&a)[16]) {
+    const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
+    // columns n1 = 0..3: elements n1, n1+4, n1+8, n1+12 -> y[n1][k2] stored back in place (a[n1 + 4*k2])
+#pragma unroll
+    for (int n1 = 0; n1 < 4; n1++) dft4(a[n1], a[n1 + 4], a[n1 + 8], a[n1 + 12]);
+    // twiddle y[n1][k2] *= w16^{n1*k2}
+    a[5] = cmul(a[5], make_float2(C1, -S1));     // n1=1,k2=1
+    a[9] = cmul(a[9], make_float2(R2, -R2));     // n1=1,k2=2
+    a[13] = cmul(a[13], make_float2(S1, -C1));   // n1=1,k2=3
+    a[6] = cmul(a[6], make_float2(R2, -R2));     // n1=2,k2=1
+    a[10] = make_float2(a[10].y, -a[10].x);      // n1=2,k2=2: w^4 = -i
+    a[14] = cmul(a[14], make_float2(-R2, -R2));  // n1=2,k2=3: w^6
+    a[7] = cmul(a[7], make_float2(S1, -C1));     // n1=3,k2=1: w^3
+    a[11] = cmul(a[11], make_float2(-R2, -R2));  // n1=3,k2=2: w^6
+    a[15] = cmul(a[15], make_float2(-C1, S1));   // n1=3,k2=3: w^9
+    // rows k2 = 0..3: over n1 -> z[k1][k2], output index j = k2 + 4*k1 lives in a[4*k2 + k1]
+#pragma unroll
+    for (int k2 = 0; k2 < 4; k2++) dft4(a[4 * k2], a[4 * k2 + 1], a[4 * k2 + 2], a[4 * k2 + 3]);
+}
+
+// Forward FFT of `nl` lines of length n stored with pitch lp (padded indexing) in x; y is scratch of the same
+// shape.  Stockham autosort, decimation in frequency:  for stage length len = r*m and stride s,
 //   y[q + s*(r*p + j)] = ( sum_k x[q + s*(p + m*k)] * w_r^{jk} ) * w_len^{p*j},   p < m, q < s.
+// Radix 16 runs in registers (one thread = one 16-point butterfly), radix 4 / 2 / generic for what is left.
 // Returns the buffer holding the result.  Ends with a __syncthreads().
 __device__ inline float2* fft_lines(float2* x, float2* y, int nl, int lp, const float2* tw, const SpecTables& t) {
     const int n = t.n;
@@ -50,30 +84,46 @@ __device__ inline float2* fft_lines(float2* x, float2* y, int nl, int lp, const 
         for (int it = threadIdx.x; it < items; it += blockDim.x) {
             const int l = it / per_line, idx = it - l * per_line;
             const int p = idx / s, q = idx - p * s;
-            const float2* xi = x + l * lp + q + s * p;
-            float2* yo = y + l * lp + q + s * r * p;
+            const float2* xl = x + l * lp;
+            float2* yl = y + l * lp;
+            const int i0 = q + s * p, o0 = q + s * r * p;
             const int sm = s * m;
-            if (r == 4) {
-                const float2 a0 = xi[0], a1 = xi[sm], a2 = xi[2 * sm], a3 = xi[3 * sm];
+            if (r == 16) {
+                float2 a[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) a[k] = xl[pidx(i0 + k * sm)];
+                dft16(a);
+                const int tp = p * s;
+                // output j = k2 + 4*k1 is in a[4*k2 + k1]
+#pragma unroll
+                for (int k1 = 0; k1 < 4; k1++)
+#pragma unroll
+                    for (int k2 = 0; k2 < 4; k2++) {
+                        const int j = k2 + 4 * k1;
+                        const float2 v = a[4 * k2 + k1];
+                        yl[pidx(o0 + j * s)] = (j == 0) ? v : cmul(v, tw[tp * j]);
+                    }
+            } else if (r == 4) {
+                const float2 a0 = xl[pidx(i0)], a1 = xl[pidx(i0 + sm)], a2 = xl[pidx(i0 + 2 * sm)], a3 = xl[pidx(i0 + 3 * sm)];
                 const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
                 const float2 b0 = cadd(t0, t2), b2 = csub(t0, t2);
                 const float2 b1 = make_float2(t1.x + t3.y, t1.y - t3.x);   // t1 - i t3
                 const float2 b3 = make_float2(t1.x - t3.y, t1.y + t3.x);   // t1 + i t3
                 const int tp = p * s;
-                yo[0] = b0;
-                yo[s] = cmul(b1, tw[tp]);
-                yo[2 * s] = cmul(b2, tw[2 * tp]);
-                yo[3 * s] = cmul(b3, tw[3 * tp]);
+                yl[pidx(o0)] = b0;
+                yl[pidx(o0 + s)] = cmul(b1, tw[tp]);
+                yl[pidx(o0 + 2 * s)] = cmul(b2, tw[2 * tp]);
+                yl[pidx(o0 + 3 * s)] = cmul(b3, tw[3 * tp]);
             } else if (r == 2) {
-                const float2 a0 = xi[0], a1 = xi[sm];
-                yo[0] = cadd(a0, a1);
-                yo[s] = cmul(csub(a0, a1), tw[p * s]);
+                const float2 a0 = xl[pidx(i0)], a1 = xl[pidx(i0 + sm)];
+                yl[pidx(o0)] = cadd(a0, a1);
+                yl[pidx(o0 + s)] = cmul(csub(a0, a1), tw[p * s]);
             } else {
                 const int wr = n / r;
                 for (int j = 0; j < r; j++) {
-                    float2 acc = xi[0];
-                    for (int k = 1; k < r; k++) acc = cadd(acc, cmul(xi[k * sm], tw[((j * k) % r) * wr]));
-                    yo[j * s] = (j == 0) ? acc : cmul(acc, tw[p * s * j]);
+                    float2 acc = xl[pidx(i0)];
+                    for (int k = 1; k < r; k++) acc = cadd(acc, cmul(xl[pidx(i0 + k * sm)], tw[((j * k) % r) * wr]));
+                    yl[pidx(o0 + j * s)] = (j == 0) ? acc : cmul(acc, tw[p * s * j]);
                 }
             }
         }
@@ -100,32 +150,32 @@ __device__ inline float2* axis_operator(float2* A, float2* B, float2* C, float2*
     if (pml > 0) {
         for (int it = threadIdx.x; it < nl * n; it += blockDim.x) {
             const int l = it / n, k = it - l * n;
-            const float2 v = F[l * lp + k];
+            const float2 v = F[l * lp + pidx(k)];
             const float mk = __ldg(t.mk + k);
-            O[l * lp + k] = make_float2(-mk * v.y, -mk * v.x);   // conj( (i k / n) * u^ )
+            O[l * lp + pidx(k)] = make_float2(-mk * v.y, -mk * v.x);   // conj( (i k / n) * u^ )
         }
         __syncthreads();
         float2* D = fft_lines(O, C, nl, lp, tw, t);
         for (int it = threadIdx.x; it < nl * 2 * pml; it += blockDim.x) {
             const int l = it / (2 * pml), mth = it - l * 2 * pml;
             const int j = (mth < pml) ? mth : n - 2 * pml + mth;
-            S[it] = cmul(__ldg(t.a + j), cconj(D[l * lp + j]));
+            S[it] = cmul(__ldg(t.a + j), cconj(D[l * lp + pidx(j)]));
         }
         __syncthreads();
     }
     // second derivative
     for (int it = threadIdx.x; it < nl * n; it += blockDim.x) {
         const int l = it / n, k = it - l * n;
-        const float2 v = F[l * lp + k];
+        const float2 v = F[l * lp + pidx(k)];
         const float ms = __ldg(t.msq + k);
-        O[l * lp + k] = make_float2(ms * v.x, -ms * v.y);        // conj( (-k^2 / n) * u^ )
+        O[l * lp + pidx(k)] = make_float2(ms * v.x, -ms * v.y);        // conj( (-k^2 / n) * u^ )
     }
     __syncthreads();
     return fft_lines(O, C, nl, lp, tw, t);
 }
 
 __device__ __forceinline__ float2 axis_value(const float2* E, const float2* S, int l, int lp, int j, const SpecTables& t) {
-    float2 v = cmul(__ldg(t.b + j), cconj(E[l * lp + j]));
+    float2 v = cmul(__ldg(t.b + j), cconj(E[l * lp + pidx(j)]));
     const int n = t.n, pml = t.pml;
     if (j < pml) v = cadd(v, S[l * 2 * pml + j]);
     else if (j >= n - pml) v = cadd(v, S[l * 2 * pml + j - (n - 2 * pml)]);
@@ -133,7 +183,7 @@ __device__ __forceinline__ float2 axis_value(const float2* E, const float2* S, i
 }
 
 __host__ __device__ inline size_t spectral_smem_bytes(int n, int lines, int pml) {
-    return (size_t)n * 8 + (size_t)3 * lines * (n + 1) * 8 + (size_t)lines * 2 * (pml > 0 ? pml : 1) * 8;
+    return (size_t)n * 8 + (size_t)3 * lines * line_pitch(n) * 8 + (size_t)lines * 2 * (pml > 0 ? pml : 1) * 8;
 }
 
 constexpr int SPEC_THREADS = 256;
@@ -141,7 +191,7 @@ constexpr int SPEC_THREADS = 256;
 __global__ void __launch_bounds__(SPEC_THREADS) spectral_rows_kernel(SpecTables t, const float2* __restrict__ u,
                                                                      float2* __restrict__ rx, int total_rows, int L) {
     HN_DYN_SMEM(float2, smem_sp);
-    const int n = t.n, lp = n + 1;
+    const int n = t.n, lp = line_pitch(n);
     float2* tw = smem_sp;
     float2* A = tw + n;
     float2* B = A + L * lp;
@@ -152,7 +202,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) spectral_rows_kernel(SpecTables 
     for (int i = threadIdx.x; i < n; i += blockDim.x) tw[i] = __ldg(t.tw + i);
     for (int it = threadIdx.x; it < nl * n; it += blockDim.x) {
         const int l = it / n, j = it - l * n;
-        A[l * lp + j] = __ldg(u + (size_t)(row0 + l) * n + j);
+        A[l * lp + pidx(j)] = __ldg(u + (size_t)(row0 + l) * n + j);
     }
     __syncthreads();
     const float2* E = axis_operator(A, B, C, S, nl, lp, tw, t);
@@ -177,7 +227,7 @@ struct ColsArgs {
 __global__ void __launch_bounds__(SPEC_THREADS) spectral_cols_kernel(SpecTables t, ColsArgs a) {
     HN_DYN_SMEM(float2, smem_sp);
     __shared__ float red[SPEC_THREADS / 32];
-    const int n = t.n, lp = n + 1, CW = a.CW;
+    const int n = t.n, lp = line_pitch(n), CW = a.CW;
     float2* tw = smem_sp;
     float2* A = tw + n;
     float2* B = A + CW * lp;
@@ -189,7 +239,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) spectral_cols_kernel(SpecTables 
     for (int i = threadIdx.x; i < n; i += blockDim.x) tw[i] = __ldg(t.tw + i);
     for (int it = threadIdx.x; it < n * CW; it += blockDim.x) {
         const int i = it / CW, c = it - i * CW;
-        if (c < nc) A[c * lp + i] = __ldg(a.u + img + (size_t)i * n + j0 + c);
+        if (c < nc) A[c * lp + pidx(i)] = __ldg(a.u + img + (size_t)i * n + j0 + c);
     }
     __syncthreads();
     const float2* E = axis_operator(A, B, C, S, nc, lp, tw, t);
