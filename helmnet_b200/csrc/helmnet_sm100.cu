@@ -213,12 +213,17 @@ static int build_tables(hn_ctx* c) {
     c->spec.pml = pml;
     factorize(n, c->spec.radix, &c->spec.nstages);
     // lines per CTA: ~48 KB of line buffers for the row pass; the column pass needs >= 32 B segments
-    int L = 4096 / n;     // ~100 KB of line buffers: two CTAs per SM
+    int L = 2048 / n;     // ~50 KB of line buffers: four CTAs per SM
+    if (const char* ev = getenv("HELMNET_SPEC_L")) L = atoi(ev);
     if (L < 1) L = 1;
     if (L > 16) L = 16;
     c->rows_L = L;
     int CW = 16;
-    while (CW > 1 && spectral_smem_bytes(n, CW, pml) > (n <= 256 ? 110 * 1024 : 200 * 1024)) CW >>= 1;
+    if (const char* ev = getenv("HELMNET_SPEC_CW")) CW = atoi(ev);
+    // ~56 KB per CTA (four CTAs per SM hide the tile-load latency; measured best at 256: L = 8, CW = 8), but keep
+    // column segments >= 32 B unless the line buffers would not fit at all
+    while (CW > 4 && spectral_smem_bytes(n, CW, pml) > 56 * 1024) CW >>= 1;
+    while (CW > 1 && spectral_smem_bytes(n, CW, pml) > 200 * 1024) CW >>= 1;
     c->cols_CW = CW;
     if (spectral_smem_bytes(n, CW, pml) > 227 * 1024) return fail(HN_ERR_ARG, "domain size too large for one line per CTA");
     return HN_OK;
