@@ -144,6 +144,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from helmnet_b200 import IterativeSolver
+    from helmnet_b200.sharding import gather_results
     from helmnet_b200.synthetic import synthetic_sos
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -217,10 +218,7 @@ def run_ours(args):
         out = solver.forward(sos_host.to(dev, non_blocking=True), num_iterations=K, return_residuals=False)
         wf, rm = out["wavefields"][0], out["residual_rmse"]
         if world > 1:   # NCCL only gathers results and residual histories
-            wl = [torch.empty_like(wf) for _ in range(world)] if rank == 0 else None
-            rl = [torch.empty_like(rm) for _ in range(world)] if rank == 0 else None
-            dist.gather(wf, wl, dst=0)
-            dist.gather(rm, rl, dst=0)
+            gathered = gather_results(wf, rm, dst=0)
         wf_host.copy_(wf, non_blocking=True)
         rm_host.copy_(rm, non_blocking=True)
 
@@ -267,8 +265,10 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": ach_tf / tf32_peak if tf32_peak else None, "traffic": None,
-                         "kernel": "UNet conv stack (37 convs, 36 launches)", "peak_source":
-                             f"{peaks['source']} bf16 burst / 2 (TF32 dense rate)", "stage_ms": st_ms[0]},
+                         "kernel": "UNet conv stack (37 convs: tcgen05 split-fp16 implicit GEMMs, fp32 TMEM accumulators)",
+                         "peak_source": f"{peaks['source']} bf16 burst / 2 (dense TF32-rate peak; the split-fp16 operands cost 3 "
+                                        "fp16-rate products per MAC, which is the same tensor time)", "stage_ms": st_ms[0],
+                         "engine": solver._engine},
             "roofline_spectral": {"bound": "hbm", "achieved": ach_gb, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                   "frac": ach_gb / peaks["hbm_gbs"], "traffic": None,
                                   "kernel": "spectral_rows_kernel + spectral_cols_kernel", "peak_source": peaks["source"],

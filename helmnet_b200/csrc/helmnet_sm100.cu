@@ -66,7 +66,7 @@ struct hn_ctx {
     double sigma_max = 0, k0 = 1, omega = 1;
     int r[kDepth + 1] = {0};
     int state_len = 0;
-    int engine = 0;
+    int engine = 1;            // 1: tcgen05 convolution kernels (default), 0: fp32 CUDA-core kernels
     // resident fields
     float *wf = nullptr, *res = nullptr, *ksq = nullptr, *src = nullptr, *rx = nullptr;
     float* state[kDepth][2] = {{nullptr}};
@@ -845,7 +845,7 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     if (const char* mr = getenv("HELMNET_TCR_MIN_RES")) c->tcr_min_res = atoi(mr);
     if (const char* mr = getenv("HELMNET_TCD_MIN_RES")) c->tcd_min_res = atoi(mr);
     if (const char* en = getenv("HELMNET_ENGINE")) c->engine = atoi(en) == 1 ? 1 : 0;
-#ifdef HN_EMU
+#ifndef HN_HAVE_TC
     c->engine = 0;
 #endif
     if (cudaMemset(c->iter_dev, 0, 16) != cudaSuccess) return cleanup(fail(HN_ERR_CUDA, "cudaMemset failed"));

@@ -181,7 +181,7 @@ class IterativeSolver(nn.Module):
         self._ctx_max_batch = 0
         self._weights_dirty = True
         self._source_dirty = True
-        self._engine = int(os.environ.get("HELMNET_ENGINE", "0"))
+        self._engine = int(os.environ.get("HELMNET_ENGINE", "1"))   # 1: tcgen05 convolutions (default), 0: fp32 CUDA cores
         self.register_buffer("sigmas", None)
         self.set_laplacian()
         self.setup_source()
