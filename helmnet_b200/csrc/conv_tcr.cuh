@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
                                 reinterpret_cast<float2*>(a.dwf_out)[pix] = make_float2(o0, o1);
                             } else {
                                 const float2 u = t == 0 ? wfa : wfb;
-                                const float2 nw = make_float2(o0 / 1e3f + u.x, o1 / 1e3f + u.y);   // hybridnet.py:570
+                                const float2 nw = make_float2(__fdividef(o0, 1e3f) + u.x, __fdividef(o1, 1e3f) + u.y);   // hybridnet.py:570 (d / 1e3 + wf)
                                 reinterpret_cast<float2*>(a.wf)[pix] = nw;
                                 lmax = fmaxf(lmax, fmaxf(fabsf(nw.x), fabsf(nw.y)));
                             }

@@ -21,6 +21,7 @@
 #include "conv_simt.cuh"
 #include "layout.cuh"
 #include "spectral.cuh"
+#include "spectral256.cuh"
 #ifndef HN_EMU
 #include "conv_tc.cuh"
 #include "conv_tcr.cuh"
@@ -89,6 +90,8 @@ struct hn_ctx {
     SpecTables spec;
     float* sigma1d = nullptr;
     int rows_L = 1, cols_CW = 1;
+    bool spec_fast = true;     // use the register-resident N = 256 spectral kernels when they apply
+    int spec_chunk = 0;        // samples per rows/cols kernel pair (0: sized to keep a chunk in L2)
     // weights
     float* wdev = nullptr;
     uint16_t* tcw = nullptr;   // fp16 split-weight images for the tcgen05 convolutions
@@ -220,6 +223,8 @@ static int build_tables(hn_ctx* c) {
     c->rows_L = L;
     int CW = 16;
     if (const char* ev = getenv("HELMNET_SPEC_CW")) CW = atoi(ev);
+    if (const char* ev = getenv("HELMNET_SPEC_CHUNK")) c->spec_chunk = atoi(ev);
+    if (const char* ev = getenv("HELMNET_SPEC_FAST")) c->spec_fast = atoi(ev) != 0;
     // ~56 KB per CTA (four CTAs per SM hide the tile-load latency; measured best at 256: L = 8, CW = 8), but keep
     // column segments >= 32 B unless the line buffers would not fit at all
     while (CW > 4 && spectral_smem_bytes(n, CW, pml) > 56 * 1024) CW >>= 1;
@@ -715,25 +720,45 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
 static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, const float* ksq, const float* src,
                            int src_batch, float* res, double* ssq, const int* slot, unsigned* amax_out = nullptr) {
     const int n = c->n;
-    const int total_rows = B * n;
     const int L = c->rows_L, CW = c->cols_CW;
-    HN_LAUNCH(spectral_rows_kernel, dim3((total_rows + L - 1) / L), dim3(SPEC_THREADS), spectral_smem_bytes(n, L, c->pml),
-              st, c->spec, reinterpret_cast<const float2*>(u), reinterpret_cast<float2*>(c->rx), total_rows, L);
-    ColsArgs a;
-    a.u = reinterpret_cast<const float2*>(u);
-    a.rx = reinterpret_cast<const float2*>(c->rx);
-    a.ksq = ksq;
-    a.src = reinterpret_cast<const float2*>(src);
-    a.res = reinterpret_cast<float2*>(res);
-    a.ssq = ssq;
-    a.slot = slot;
-    a.amax_out = amax_out;
-    a.src_batch = src_batch;
-    a.B = B;
-    a.CW = CW;
-    HN_LAUNCH(spectral_cols_kernel, dim3((n + CW - 1) / CW, B), dim3(SPEC_THREADS), spectral_smem_bytes(n, CW, c->pml), st,
-              c->spec, a);
-    c->launches += 2;
+    // Row and column passes alternate over chunks of samples small enough that u, rx and k_sq of a chunk stay in the
+    // 126 MB L2 between the two kernels (20 B per point), so the column pass re-reads them from L2, not HBM.
+    // (Measured at 256^2 x 256: not worth it -- 0.70 ms unchunked vs 0.77 ms in chunks of 64; the kernels are bound by
+    // their shared-memory FFT passes, not by HBM, so the default is one pair of launches.)
+    int chunk = c->spec_chunk > 0 ? c->spec_chunk : B;
+    if (chunk < 1) chunk = 1;
+    if (chunk > B) chunk = B;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = (B - b0 < chunk) ? B - b0 : chunk;
+        const size_t off = (size_t)b0 * n * n;
+        const int total_rows = nb * n;
+        const bool fast256 = (n == 256 && c->pml <= 16 && c->spec_fast);
+        if (fast256)
+            HN_LAUNCH(s256::spectral_rows256_kernel, dim3((total_rows + s256::LINES - 1) / s256::LINES), dim3(s256::THREADS), 0, st,
+                      c->spec, reinterpret_cast<const float2*>(u) + off, reinterpret_cast<float2*>(c->rx) + off, total_rows);
+        else
+            HN_LAUNCH(spectral_rows_kernel, dim3((total_rows + L - 1) / L), dim3(SPEC_THREADS), spectral_smem_bytes(n, L, c->pml), st,
+                      c->spec, reinterpret_cast<const float2*>(u) + off, reinterpret_cast<float2*>(c->rx) + off, total_rows, L);
+        ColsArgs a;
+        a.u = reinterpret_cast<const float2*>(u) + off;
+        a.rx = reinterpret_cast<const float2*>(c->rx) + off;
+        a.ksq = ksq ? ksq + off : nullptr;
+        a.src = src ? reinterpret_cast<const float2*>(src) + (src_batch > 1 ? off : 0) : nullptr;
+        a.res = reinterpret_cast<float2*>(res) + off;
+        a.ssq = ssq;
+        a.slot = slot;
+        a.amax_out = amax_out;
+        a.src_batch = src_batch;
+        a.B = B;
+        a.b0 = b0;
+        a.CW = CW;
+        if (fast256)
+            HN_LAUNCH(s256::spectral_cols256_kernel, dim3(n / s256::LINES, nb), dim3(s256::THREADS), 0, st, c->spec, a);
+        else
+            HN_LAUNCH(spectral_cols_kernel, dim3((n + CW - 1) / CW, nb), dim3(SPEC_THREADS), spectral_smem_bytes(n, CW, c->pml), st,
+                      c->spec, a);
+        c->launches += 2;
+    }
     return HN_OK;
 }
 

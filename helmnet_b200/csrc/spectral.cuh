@@ -222,6 +222,7 @@ struct ColsArgs {
     const int* slot;      // device scalar: which ssq slot (iteration index)
     unsigned* amax_out;   // running max |res| slot (publish_amax) or null
     int src_batch, B, CW;
+    int b0;               // first sample of this launch (ssq is indexed by the absolute sample)
 };
 
 __global__ void __launch_bounds__(SPEC_THREADS) spectral_cols_kernel(SpecTables t, ColsArgs a) {
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) spectral_cols_kernel(SpecTables 
         if (threadIdx.x == 0) {
             float tot = 0.f;
             for (int w = 0; w < SPEC_THREADS / 32; w++) tot += red[w];
-            atomicAdd(a.ssq + (size_t)(*a.slot) * a.B + b, (double)tot);
+            atomicAdd(a.ssq + (size_t)(*a.slot) * a.B + a.b0 + b, (double)tot);
         }
     }
 }

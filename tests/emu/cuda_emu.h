@@ -81,6 +81,7 @@ uint32_t shfl_exchange(uint32_t v, int src_lane_of_self_fn_kind, int arg);
 #define gridDim hn_emu::g_gridDim
 
 static inline void __syncthreads() { hn_emu::yield_wait(1); }
+static inline void __syncwarp() { hn_emu::shfl_exchange(0u, 0, 0); }
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
 static inline double atomicAdd(double* p, double v) { double o = *p; *p = o + v; return o; }

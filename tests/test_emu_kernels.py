@@ -24,6 +24,28 @@ def test_laplacian_generic_radix(emu_solver):
     assert rel_l2(emu_solver.Lap(u), O.laplacian(u, O.make_operator(80, 8, 2.0, 1.0))) < 1e-6
 
 
+@pytest.mark.parametrize("pml", [8, 12, 0])
+def test_laplacian_n256_register_fft(emu_solver, pml):
+    """N = 256 takes the register-resident 16 x 16 kernels (spectral256.cuh); pml 12 has threads owning two strip samples."""
+    from oracle import helmnet_oracle as O
+    old = emu_solver.hparams.PMLsize
+    emu_solver.hparams.PMLsize = pml
+    try:
+        emu_solver.set_domain_size(256, source_location=[30, 128])
+        u = torch.randn(1, 256, 256, 2, generator=torch.Generator().manual_seed(5))
+        ref = O.laplacian(u, O.make_operator(256, pml, 2.0, 1.0)) if pml > 0 else None
+        out = emu_solver.Lap(u)
+        if pml > 0:
+            assert rel_l2(out, ref) < 1e-6
+        else:   # no PML: plain spectral Laplacian
+            k = torch.tensor(O.wavenumbers(256)).float()
+            uf = torch.fft.fftn(torch.view_as_complex(u), dim=(-2, -1))
+            lap = torch.view_as_real(torch.fft.ifftn(-(k[None, :, None] ** 2 + k[None, None, :] ** 2) * uf, dim=(-2, -1)))
+            assert rel_l2(out, lap) < 1e-6
+    finally:
+        emu_solver.hparams.PMLsize = old
+
+
 def test_unet_and_single_step(emu_solver, gold):
     g = gold("unet_step_n32.npz")
     s = emu_solver
