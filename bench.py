@@ -200,7 +200,7 @@ def run_ours(args):
     ms_max = float(t.item())
     value = b_total * n * n * K / (ms_max * 1e-3) / 1e6
 
-    # ---------------- per-stage device time (events around the two stages of one iteration) ---------
+    # ---------------- per-stage and per-kernel device time (CUDA events on the launch stream) -------------
     import ctypes as C
     stage = (C.c_float * 2)()
     st_ms = [0.0, 0.0]
@@ -209,6 +209,20 @@ def run_ours(args):
         lib.check(lib.hn_profile_iteration(ctx, stage, stream()), "hn_profile_iteration")
         st_ms[0] += stage[0] / reps
         st_ms[1] += stage[1] / reps
+    # algorithmic HBM bytes per level-0 point and launch: activations are NHWC8 fp32 = 32 B
+    kernel_table = [
+        (0, "conv3x3_tcr_kernel<SRC_A8> (inc conv #2, 8->8, level 0)", 32 + 32),
+        (1, "conv3x3_tcr_kernel<SRC_A8_B8> (decode[0] conv #1, 16->8, level 0)", 64 + 32),
+        (2, "down_tcr_kernel (enc[0].down, level 0 -> 1)", 32 + 8),
+        (3, "up_tcr_kernel (up[0], level 1 -> 0)", 8 + 32),
+        (4, "spectral_rows256_kernel" if n == 256 else "spectral_rows_kernel", 8 + 8),
+        (5, "spectral_cols256_kernel" if n == 256 else "spectral_cols_kernel", 8 + 8 + 4 + 8),
+    ]
+    kern_ms = {}
+    one = C.c_float()
+    for which, _, _ in kernel_table:
+        lib.check(lib.hn_profile_layer(ctx, which, 10, C.byref(one), stream()), "hn_profile_layer")
+        kern_ms[which] = float(one.value)
 
     # ---------------- end to end through the public API: `e2e` ----------------------------------------
     wf_host = torch.empty(b_local, 2, n, n).pin_memory()
@@ -243,6 +257,13 @@ def run_ours(args):
         tf32_peak = peaks["bf16_tflops"] / 2.0
         ach_tf = FLOP_PER_POINT * pts / t_unet / 1e12 if t_unet > 0 else 0.0
         ach_gb = BYTES_PER_POINT_SPECTRAL * pts / t_spec / 1e9 if t_spec > 0 else 0.0
+        roof = []
+        for which, name, bpp in kernel_table:
+            ms_k = kern_ms[which]
+            gbs = bpp * pts / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
+            roof.append({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                         "traffic": None, "kernel": name, "ms_per_launch": ms_k, "algorithmic_bytes_per_point": bpp,
+                         "peak_source": f"{peaks['source']} (MEASURED_PEAKS.json hbm_gbs, burst copy)"})
         cpu = None
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -263,16 +284,16 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "kernels_per_iteration": int(lib.hn_kernels_per_iteration(ctx)),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": tf32_peak, "unit": "TFLOP/s",
-                         "frac": ach_tf / tf32_peak if tf32_peak else None, "traffic": None,
-                         "kernel": "UNet conv stack (37 convs: tcgen05 split-fp16 implicit GEMMs, fp32 TMEM accumulators)",
-                         "peak_source": f"{peaks['source']} bf16 burst / 2 (dense TF32-rate peak; the split-fp16 operands cost 3 "
-                                        "fp16-rate products per MAC, which is the same tensor time)", "stage_ms": st_ms[0],
-                         "engine": solver._engine},
-            "roofline_spectral": {"bound": "hbm", "achieved": ach_gb, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                  "frac": ach_gb / peaks["hbm_gbs"], "traffic": None,
-                                  "kernel": "spectral_rows_kernel + spectral_cols_kernel", "peak_source": peaks["source"],
-                                  "stage_ms": st_ms[1], "algorithmic_bytes_per_point": BYTES_PER_POINT_SPECTRAL},
+            "roofline": roof[0],
+            "roofline_kernels": roof[1:],
+            "roofline_stage_unet": {"bound": "tensor", "achieved": ach_tf, "peak": tf32_peak, "unit": "TFLOP/s",
+                                    "frac": ach_tf / tf32_peak if tf32_peak else None, "stage_ms": st_ms[0],
+                                    "note": "16103.25 FLOP/point over the whole conv stack vs the dense TF32-rate peak "
+                                            f"({peaks['source']} bf16 burst / 2); the C_out=8 GEMMs are HBM-bound, see `roofline`",
+                                    "engine": solver._engine},
+            "roofline_stage_spectral": {"bound": "hbm", "achieved": ach_gb, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                        "frac": ach_gb / peaks["hbm_gbs"], "stage_ms": st_ms[1],
+                                        "algorithmic_bytes_per_point": BYTES_PER_POINT_SPECTRAL},
             "cpu_baseline": cpu,
             "final_rmse_max": float(rmse_buf[K - 1].max().item()),
         }

@@ -43,6 +43,7 @@ _SIGS = {
     "hn_debug_tensor": (C.c_int, [_P, C.c_char_p, _P, C.c_int, _P]),
     "hn_set_engine": (C.c_int, [_P, C.c_int]),
     "hn_sync_check": (C.c_int, [_P, _P]),
+    "hn_profile_layer": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float), _P]),
     "hn_profile_iteration": (C.c_int, [_P, C.POINTER(C.c_float), _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -573,6 +573,95 @@ static int set_smem_attrs(hn_ctx* c) {
 }
 #endif
 
+static int launch_down(hn_ctx* c, int d, int B, cudaStream_t st) {
+    const Weights& W = c->W;
+    const int r = c->r[d];
+    DownArgs dn;
+    dn.in = c->skip[d];
+    dn.w = c->wdev + W.down[d].w;
+    dn.bias = c->wdev + W.down[d].b;
+    dn.out = c->x[d + 1];
+    dn.amax_out = c->amax + S_X + d + 1;
+    dn.H = r;
+    dn.W = r;
+#ifdef HN_HAVE_TC
+    if (c->engine == 1 && W.down[d].tcr != (size_t)-1 && r / 2 >= c->tcd_min_res) {
+        static bool tcd_attr_done[16] = {false};
+        if (!tcd_attr_done[c->device & 15]) {
+            HN_CUDA(cudaFuncSetAttribute(tcd::down_tcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcd::SMEM_BYTES));
+            tcd_attr_done[c->device & 15] = true;
+        }
+        tcd::Args t;
+        t.in = c->skip[d];
+        t.bmat = reinterpret_cast<const __half*>(c->tcw + W.down[d].tcr);
+        t.bias = c->wdev + W.down[d].b;
+        t.out = c->x[d + 1];
+        t.amax_in = c->amax + S_SKIP + d;
+        t.amax_out = c->amax + S_X + d + 1;
+        t.error_flag = c->err_flag;
+        t.w_inv_scale = W.down[d].tc_inv;
+        t.H = r;
+        t.W = r;
+        t.nsx = (r / 2 + tcr::CW - 1) / tcr::CW;
+        t.nsy = (r / 2 + tcd::ROWS_O - 1) / tcd::ROWS_O;
+        t.total_strips = t.nsx * t.nsy * B;
+        const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;
+        tcd::down_tcr_kernel<<<dim3(tgrid), dim3(tcr::THREADS), tcd::SMEM_BYTES, st>>>(t);
+        c->launches++;
+        return HN_OK;
+    }
+#endif
+    dim3 g((r / 2 + DN_TX - 1) / DN_TX, (r / 2 + DN_TY - 1) / DN_TY, B);
+    HN_LAUNCH(down_kernel, g, dim3(DN_THREADS), DN_SMEM, st, dn);
+    c->launches++;
+    return HN_OK;
+}
+
+static int launch_up(hn_ctx* c, int d, int B, cudaStream_t st) {
+    const Weights& W = c->W;
+    const int r = c->r[d];
+    UpArgs up;
+    up.in = (d == kDepth - 1) ? c->bot : c->dec[d + 1];
+    up.w = c->wdev + W.up[d].w;
+    up.bias = c->wdev + W.up[d].b;
+    up.out = c->upo[d];
+    up.amax_out = c->amax + S_UPO + d;
+    up.Hi = r / 2;
+    up.Wi = r / 2;
+#ifdef HN_HAVE_TC
+    if (c->engine == 1 && W.up[d].tcr != (size_t)-1 && r / 2 >= c->tcd_min_res && ((r / 2) % 2) == 0) {
+        static bool tcu_attr_done[16] = {false};
+        if (!tcu_attr_done[c->device & 15]) {
+            HN_CUDA(cudaFuncSetAttribute(tcu::up_tcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcu::SMEM_BYTES));
+            tcu_attr_done[c->device & 15] = true;
+        }
+        tcu::Args t;
+        t.in = up.in;
+        t.bmat = reinterpret_cast<const __half*>(c->tcw + W.up[d].tcr);
+        t.bias = up.bias;
+        t.out = up.out;
+        t.amax_in = c->amax + ((d == kDepth - 1) ? S_BOT : S_DEC + d + 1);
+        t.amax_out = up.amax_out;
+        t.error_flag = c->err_flag;
+        t.w_inv_scale = W.up[d].tc_inv;
+        t.Hi = r / 2;
+        t.Wi = r / 2;
+        t.nsx = (r / 2 + tcr::CW - 1) / tcr::CW;
+        t.nsy = (r / 2 + tcu::ROWS_I - 1) / tcu::ROWS_I;
+        t.total_strips = t.nsx * t.nsy * B;
+        const int tgrid = t.total_strips < c->num_sms ? t.total_strips : c->num_sms;   // one CTA per SM (owns all 512 TMEM columns)
+        tcu::up_tcr_kernel<<<dim3(tgrid), dim3(tcr::THREADS), tcu::SMEM_BYTES, st>>>(t);
+        c->launches++;
+    } else
+#endif
+    {
+        dim3 g((r / 2 + UP_TL - 1) / UP_TL, (r / 2 + UP_TL - 1) / UP_TL, B);
+        HN_LAUNCH(up_kernel, g, dim3(UP_THREADS), UP_SMEM, st, up);
+        c->launches++;
+    }
+    return HN_OK;
+}
+
 // HybridNet.forward (architectures.py:439-465).  `from_in6`: read the 6-channel input from c->in6 instead of
 // building it from (wf, 1e3*res, sigmas); `raw_out`: store the network output to c->dwf instead of updating wf.
 static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool raw_out) {
@@ -609,44 +698,7 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
         HN_TRY((launch_conv3<SRC_A8_B2, 2, true, EPI_STORE>(c, t0, B, st)));
         Conv3Args t1 = conv_args(c, W.sta[d][1], c->mid2[d], nullptr, c->state[d][nxt], r, S_STATE + 2 * d + nxt);
         HN_TRY((launch_conv3<SRC_A2, 2, false, EPI_STORE>(c, t1, B, st)));
-        DownArgs dn;
-        dn.in = c->skip[d];
-        dn.w = c->wdev + W.down[d].w;
-        dn.bias = c->wdev + W.down[d].b;
-        dn.out = c->x[d + 1];
-        dn.amax_out = c->amax + S_X + d + 1;
-        dn.H = r;
-        dn.W = r;
-#ifdef HN_HAVE_TC
-        if (c->engine == 1 && W.down[d].tcr != (size_t)-1 && r / 2 >= c->tcd_min_res) {
-            static bool tcd_attr_done[16] = {false};
-            if (!tcd_attr_done[c->device & 15]) {
-                HN_CUDA(cudaFuncSetAttribute(tcd::down_tcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcd::SMEM_BYTES));
-                tcd_attr_done[c->device & 15] = true;
-            }
-            tcd::Args t;
-            t.in = c->skip[d];
-            t.bmat = reinterpret_cast<const __half*>(c->tcw + W.down[d].tcr);
-            t.bias = c->wdev + W.down[d].b;
-            t.out = c->x[d + 1];
-            t.amax_in = c->amax + S_SKIP + d;
-            t.amax_out = c->amax + S_X + d + 1;
-            t.error_flag = c->err_flag;
-            t.w_inv_scale = W.down[d].tc_inv;
-            t.H = r;
-            t.W = r;
-            t.nsx = (r / 2 + tcr::CW - 1) / tcr::CW;
-            t.nsy = (r / 2 + tcd::ROWS_O - 1) / tcd::ROWS_O;
-            t.total_strips = t.nsx * t.nsy * B;
-            const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;
-            tcd::down_tcr_kernel<<<dim3(tgrid), dim3(tcr::THREADS), tcd::SMEM_BYTES, st>>>(t);
-            c->launches++;
-            continue;
-        }
-#endif
-        dim3 g((r / 2 + DN_TX - 1) / DN_TX, (r / 2 + DN_TY - 1) / DN_TY, B);
-        HN_LAUNCH(down_kernel, g, dim3(DN_THREADS), DN_SMEM, st, dn);
-        c->launches++;
+        HN_TRY(launch_down(c, d, B, st));
     }
     // bottom
     {
@@ -659,45 +711,7 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
     // decoder
     for (int d = kDepth - 1; d >= 0; d--) {
         const int r = c->r[d];
-        UpArgs up;
-        up.in = (d == kDepth - 1) ? c->bot : c->dec[d + 1];
-        up.w = c->wdev + W.up[d].w;
-        up.bias = c->wdev + W.up[d].b;
-        up.out = c->upo[d];
-        up.amax_out = c->amax + S_UPO + d;
-        up.Hi = r / 2;
-        up.Wi = r / 2;
-#ifdef HN_HAVE_TC
-        if (c->engine == 1 && W.up[d].tcr != (size_t)-1 && r / 2 >= c->tcd_min_res && ((r / 2) % 2) == 0) {
-            static bool tcu_attr_done[16] = {false};
-            if (!tcu_attr_done[c->device & 15]) {
-                HN_CUDA(cudaFuncSetAttribute(tcu::up_tcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcu::SMEM_BYTES));
-                tcu_attr_done[c->device & 15] = true;
-            }
-            tcu::Args t;
-            t.in = up.in;
-            t.bmat = reinterpret_cast<const __half*>(c->tcw + W.up[d].tcr);
-            t.bias = up.bias;
-            t.out = up.out;
-            t.amax_in = c->amax + ((d == kDepth - 1) ? S_BOT : S_DEC + d + 1);
-            t.amax_out = up.amax_out;
-            t.error_flag = c->err_flag;
-            t.w_inv_scale = W.up[d].tc_inv;
-            t.Hi = r / 2;
-            t.Wi = r / 2;
-            t.nsx = (r / 2 + tcr::CW - 1) / tcr::CW;
-            t.nsy = (r / 2 + tcu::ROWS_I - 1) / tcu::ROWS_I;
-            t.total_strips = t.nsx * t.nsy * B;
-            const int tgrid = t.total_strips < c->num_sms ? t.total_strips : c->num_sms;   // one CTA per SM (owns all 512 TMEM columns)
-            tcu::up_tcr_kernel<<<dim3(tgrid), dim3(tcr::THREADS), tcu::SMEM_BYTES, st>>>(t);
-            c->launches++;
-        } else
-#endif
-        {
-            dim3 g((r / 2 + UP_TL - 1) / UP_TL, (r / 2 + UP_TL - 1) / UP_TL, B);
-            HN_LAUNCH(up_kernel, g, dim3(UP_THREADS), UP_SMEM, st, up);
-            c->launches++;
-        }
+        HN_TRY(launch_up(c, d, B, st));
         // mid[d] is reused as scratch by inc / encoder / decoder; each use has its own amax slot
         Conv3Args d0 = conv_args(c, W.dec[d][0], c->upo[d], c->skip[d], c->mid[d], r, S_DMID + d, S_UPO + d, S_SKIP + d);
         HN_TRY((launch_conv3<SRC_A8_B8, 8, true, EPI_STORE>(c, d0, B, st)));
@@ -1278,6 +1292,86 @@ int hn_sync_check(hn_ctx* c, void* stream) {
     int flag = 0;
     HN_CUDA(cudaMemcpy(&flag, c->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
     if (flag != 0) return fail(HN_ERR_CUDA, "tcgen05 watchdog: an MMA completion barrier was never signalled");
+#endif
+    return HN_OK;
+}
+
+// Average device time (CUDA events on `stream`) of `reps` back-to-back launches of ONE kernel of the iteration on the
+// context's current buffers:  which = 0: inc conv #2 (8->8, level 0)   1: decode[0] conv #1 (16->8, level 0)
+//   2: enc[0].down   3: up[0]   4: spectral rows   5: spectral cols.   Used by bench.py for the per-kernel roofline.
+int hn_profile_layer(hn_ctx* c, int which, int reps, float* out_ms, void* stream) {
+    if (!c || !out_ms || reps < 1) return fail(HN_ERR_ARG, "bad argument");
+    if (!c->problem_set) return fail(HN_ERR_STATE, "no solve state");
+    *out_ms = 0.f;
+#ifndef HN_EMU
+    cudaStream_t st = (cudaStream_t)stream;
+    const Weights& W = c->W;
+    const int B = c->batch, cur = c->cur;
+    cudaEvent_t e0, e1;
+    HN_CUDA(cudaEventCreate(&e0));
+    HN_CUDA(cudaEventCreate(&e1));
+    int rc = HN_OK;
+    for (int i = -1; i < reps && rc == HN_OK; i++) {   // i = -1: untimed warm-up launch
+        if (i == 0) cudaEventRecord(e0, st);
+        switch (which) {
+            case 0: {
+                Conv3Args a = conv_args(c, W.inc[1], c->mid[0], nullptr, c->x[0], c->r[0], S_X + 0, S_IMID);
+                rc = launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, a, B, st);
+            } break;
+            case 1: {
+                Conv3Args a = conv_args(c, W.dec[0][0], c->upo[0], c->skip[0], c->mid[0], c->r[0], S_DMID + 0, S_UPO + 0, S_SKIP + 0);
+                rc = launch_conv3<SRC_A8_B8, 8, true, EPI_STORE>(c, a, B, st);
+            } break;
+            case 2: rc = launch_down(c, 0, B, st); break;
+            case 3: rc = launch_up(c, 0, B, st); break;
+            case 4:
+            case 5: {
+                const int n = c->n;
+                const bool fast256 = (n == 256 && c->pml <= 16 && c->spec_fast);
+                if (which == 4) {
+                    const int total_rows = B * n;
+                    if (fast256)
+                        s256::spectral_rows256_kernel<<<dim3((total_rows + s256::LINES - 1) / s256::LINES), dim3(s256::THREADS), 0, st>>>(
+                            c->spec, reinterpret_cast<const float2*>(c->wf), reinterpret_cast<float2*>(c->rx), total_rows);
+                    else
+                        spectral_rows_kernel<<<dim3((total_rows + c->rows_L - 1) / c->rows_L), dim3(SPEC_THREADS),
+                                               spectral_smem_bytes(n, c->rows_L, c->pml), st>>>(
+                            c->spec, reinterpret_cast<const float2*>(c->wf), reinterpret_cast<float2*>(c->rx), total_rows, c->rows_L);
+                } else {
+                    ColsArgs a;
+                    a.u = reinterpret_cast<const float2*>(c->wf);
+                    a.rx = reinterpret_cast<const float2*>(c->rx);
+                    a.ksq = c->ksq;
+                    a.src = reinterpret_cast<const float2*>(c->src);
+                    a.res = reinterpret_cast<float2*>(c->tmp2b);
+                    a.ssq = nullptr;
+                    a.slot = c->iter_dev + 1;
+                    a.amax_out = nullptr;
+                    a.src_batch = c->src_batch;
+                    a.B = B;
+                    a.b0 = 0;
+                    a.CW = c->cols_CW;
+                    if (fast256) s256::spectral_cols256_kernel<<<dim3(n / s256::LINES, B), dim3(s256::THREADS), 0, st>>>(c->spec, a);
+                    else
+                        spectral_cols_kernel<<<dim3((n + a.CW - 1) / a.CW, B), dim3(SPEC_THREADS), spectral_smem_bytes(n, a.CW, c->pml), st>>>(
+                            c->spec, a);
+                }
+            } break;
+            default: rc = fail(HN_ERR_ARG, "unknown kernel id");
+        }
+    }
+    (void)cur;
+    if (rc == HN_OK) {
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *out_ms = ms / (float)reps;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    HN_TRY(rc);
+    HN_CUDA(cudaGetLastError());
 #endif
     return HN_OK;
 }

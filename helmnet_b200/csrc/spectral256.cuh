@@ -127,6 +127,13 @@ __global__ void __launch_bounds__(THREADS) spectral_cols256_kernel(SpecTables t,
         const int i = it >> 3, c = it & 7;
         tile[i * TILE_P + c] = __ldg(a.u + img + (size_t)i * N + j0 + c);
     }
+#ifndef HN_EMU
+    // the epilogue's operands (rx, k_sq) are fetched towards L2 now so that their latency hides behind the transforms
+    for (int i = threadIdx.x; i < N; i += THREADS) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rx + img + (size_t)i * N + j0));
+        if (a.ksq != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ksq + img + (size_t)i * N + j0));
+    }
+#endif
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = lane & 15, ll = warp * 2 + (lane >> 4);

@@ -124,6 +124,9 @@ int hn_set_engine(hn_ctx* ctx, int engine);
 /* Synchronises `stream` and reports device-side faults recorded by the kernels (tcgen05 completion
  * watchdog). Returns HN_OK or HN_ERR_CUDA. */
 int hn_sync_check(hn_ctx* ctx, void* stream);
+/* Average device time in ms of `reps` launches of one kernel of the iteration on the current buffers
+ * (which = 0 inc conv #2, 1 decode[0] conv #1, 2 enc[0].down, 3 up[0], 4 spectral rows, 5 spectral cols). Synchronous. */
+int hn_profile_layer(hn_ctx* ctx, int which, int reps, float* out_ms, void* stream);
 /* Per-stage device time of the last hn_profile_iteration() in milliseconds:
  * out[0] = UNet stage, out[1] = spectral residual stage. Synchronous; runs ONE iteration. */
 int hn_profile_iteration(hn_ctx* ctx, float out_ms[2], void* stream);
