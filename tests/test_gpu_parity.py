@@ -128,7 +128,8 @@ def test_trajectory_source_maps_golden(cuda_solver, gold):
     assert rel_l2(out["wavefields"][0], g["wavefield"]) < PER_ITER_TOL
 
 
-@pytest.mark.parametrize("n,b,iters", [(96, 32, 25), (48, 3, 10), (112, 2, 6), (512, 2, 6)])
+@pytest.mark.parametrize("n,b,iters", [(96, 32, 25), (48, 3, 10), (112, 2, 6), (512, 2, 6), (128, 2, 5), (80, 1, 5), (16, 2, 5),
+                                       (1024, 1, 3)])
 def test_forward_vs_oracle(cuda_solver, f_weights, n, b, iters):
     """Seeded synthetic maps (config[1] shape 96^2 x 32 included), per-iteration bar at every iteration."""
     from helmnet_b200.synthetic import synthetic_sos
@@ -175,3 +176,47 @@ def test_launch_accounting(cuda_solver):
     before = s.lib.hn_launch_count(s._ctx)
     s.forward(torch.ones(1, 1, 64, 64).cuda(), num_iterations=5, return_residuals=False)
     assert s.lib.hn_launch_count(s._ctx) - before >= 5 * k
+
+
+def test_n_steps_and_variable_source(cuda_solver, gold):
+    """Public variants of the loop: n_steps continues a solve bit-for-bit (SIMT) / to round-off (tcgen05);
+    forward_variable_src == forward + source swap + residual recompute + n_steps (reference hybridnet.py:699-754)."""
+    g = gold("traj_srcmap_n64.npz")
+    s = cuda_solver
+    src = torch.tensor(g["source"]).cuda()
+    sos = torch.tensor(g["sos"]).cuda()
+    s.set_domain_size(64, source_map=src)
+    out = s.forward(sos, num_iterations=6, return_wavefields=True, return_states=True)
+    k_sq, _ = s.get_initials(sos)
+    s.f.set_states(out["states"][2], flatten=True)
+    cont = s.n_steps(out["wavefields"][2], k_sq, out["residuals"][2], 3)
+    assert rel_l2(cont["wavefields"][0], out["wavefields"][5]) < 1e-6
+    assert rel_l2(s.f.get_states(flatten=True), out["states"][5]) < 1e-5
+    a = s.forward_variable_src(sos, {"iteration": [2], "src_maps": [2 * src]}, num_iterations=4)
+    s.set_source_maps(src)
+    o = s.forward(sos, num_iterations=2)
+    s.set_source_maps(2 * src)
+    res = s.get_residual(o["wavefields"][0], k_sq)
+    b = s.n_steps(o["wavefields"][0], k_sq, res, 2)
+    assert rel_l2(a["wavefields"][0], b["wavefields"][0]) < 1e-6
+    assert a["residual_rmse"].shape == (4, 3)
+
+
+def test_large_amplitude_inputs_stay_in_range(cuda_solver, f_weights):
+    """The fp16 operand split must not overflow: source amplitude 1e4 puts 1e3*residual at 1e7 (fp16 max is 65504)."""
+    from oracle import helmnet_oracle as O
+    s, n = cuda_solver, 64
+    loc = [20, 30]
+    old = s.hparams.source_amplitude
+    s.hparams.source_amplitude = 1e4
+    try:
+        s.set_domain_size(n, source_location=loc)
+        sos = torch.ones(1, 1, n, n)
+        orc = O.Oracle(f_weights, n)
+        orc.set_source(O.point_source(n, loc, amplitude=1e4))
+        ref = orc.forward(sos, 3, keep_wavefields=True)
+        out = s.forward(sos.cuda(), num_iterations=3, return_wavefields=True)
+        assert torch.isfinite(out["wavefields"][2]).all()
+        assert max(rel_l2(out["wavefields"][k], ref["wavefields"][k]) for k in range(3)) < PER_ITER_TOL
+    finally:
+        s.hparams.source_amplitude = old
