@@ -123,6 +123,13 @@ class HybridNet(nn.Module):
         b, c = h_flatten.shape[0], h_flatten.shape[1]
         return [h_flatten[:, :, lo:hi].reshape(b, c, s, s) for (lo, hi), s in zip(self.state_boundaries, self.states_dimension)]
 
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        res = super().load_state_dict(state_dict, strict=strict, **kw)
+        owner = self._owner() if self._owner is not None else None
+        if owner is not None:
+            owner.sync_weights()          # evaluate.py:62 copies weights with new_model.f.load_state_dict(...)
+        return res
+
     def weight_blob(self) -> torch.Tensor:
         """The 48,160 parameters in state_dict order, the layout hn_load_weights expects."""
         return torch.cat([v.detach().reshape(-1).float().cpu() for v in self.state_dict().values()]).contiguous()
@@ -472,6 +479,23 @@ class IterativeSolver(nn.Module):
             "last_iteration": last_iteration,
             "residual_rmse": rmse,
         }
+
+    # ---- test-set evaluation hooks (reference hybridnet.py:299-330, driven by evaluate.py:27-29) ------------------
+    def test_step(self, batch, batch_idx=0):
+        self.reset_source()
+        output = self.forward(batch, num_iterations=self.hparams.max_iterations, return_wavefields=True, return_states=False,
+                              return_residuals=False)
+        return {"losses": output["residual_rmse"].transpose(0, 1).contiguous(), "wavefields": list(output["wavefields"])}
+
+    def test_epoch_end(self, outputs, out_dir: str = "results"):
+        """Writes the two files produce_figures.py:51-64 consumes."""
+        import os
+        os.makedirs(out_dir, exist_ok=True)
+        all_losses = torch.cat([o["losses"] for o in outputs], dim=0).cpu().numpy()
+        np.save(os.path.join(out_dir, "evolution_of_model_RMSE_on_test_set"), all_losses)
+        wavefields = torch.cat([torch.stack(o["wavefields"], 0) for o in outputs], 1).permute(1, 0, 2, 3, 4)
+        np.save(os.path.join(out_dir, "evolution_of_wavefields_on_test_set"), wavefields.cpu().numpy())
+        return all_losses
 
     def single_step(self, wavefield, k_sq, residual, get_residual: bool = True):
         out = self.n_steps(wavefield, k_sq, residual, 1)

@@ -93,3 +93,23 @@ def test_forward_variable_src(emu_solver, gold):
     b = s.n_steps(o["wavefields"][0], k_sq, res, 2)
     assert rel_l2(a["wavefields"][0], b["wavefields"][0]) < 1e-6
     assert a["residual_rmse"].shape == (4, 3)
+
+
+def test_evaluation_driver_outputs(tmp_path, gold):
+    """evaluate.py flow (get_model -> test_step -> test_epoch_end) writes the two result files with the reference's shapes."""
+    import numpy as np
+    from conftest import CKPT
+    from emu_backend import EmuLib
+    from helmnet_b200 import IterativeSolver, evaluate
+    model = evaluate.get_model(CKPT, domain_size=32, source_location=[10, 16])
+    model._backend = EmuLib()
+    assert model.hparams.domain_size == 32 and model.source.shape == (1, 2, 32, 32)
+    sos = torch.ones(3, 1, 32, 32)
+    sos[:, :, 10:20, 5:25] = 1.4
+    losses = evaluate.results_on_test_set(model, sos, batch_size=2, out_dir=str(tmp_path), max_iterations=4)
+    a = np.load(tmp_path / "evolution_of_model_RMSE_on_test_set.npy")
+    w = np.load(tmp_path / "evolution_of_wavefields_on_test_set.npy")
+    assert a.shape == (3, 4) and w.shape == (3, 4, 2, 32, 32) and np.array_equal(a, losses)
+    # same numbers as a direct forward
+    ref = model.forward(sos, num_iterations=4, return_wavefields=True)
+    assert rel_l2(torch.tensor(w[:, 3]), ref["wavefields"][3]) < 1e-6
