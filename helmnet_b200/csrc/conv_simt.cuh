@@ -451,4 +451,72 @@ __global__ void __launch_bounds__(UP_THREADS) up_kernel(UpArgs a) {
     publish_amax(a.amax_out, lmax);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// conv_state second convolution: Conv2d(2, 2, 3, padding 1) on the 2-channel hidden-state intermediate
+// (architectures.py:213-217, second layer of conv_state's DoubleConv).  36 MACs and 16 bytes per pixel: purely
+// bandwidth bound, so a lean kernel: float2 tile in shared memory, each thread a 2 x 4 pixel patch from a 4 x 6
+// register window (3 shared-memory loads per output pixel instead of 9).
+// ------------------------------------------------------------------------------------------------------
+struct State2Args {
+    const float* in;      // float2 [B][H][W]
+    const float* w;       // [co 2][ci 2][3][3] as stored in the checkpoint
+    const float* bias;    // [2]
+    float* out;           // float2 [B][H][W]
+    unsigned* amax_out;
+    int H, W;
+};
+constexpr int S2_TX = 64, S2_TY = 32, S2_THREADS = 256;   // thread (tx 0..15, ty 0..15) -> pixels x = 4 tx.., y = 2 ty..
+constexpr int S2_PITCH = S2_TX + 2;
+
+__global__ void __launch_bounds__(S2_THREADS) state2_kernel(State2Args a) {
+    __shared__ float2 tile[(S2_TY + 2) * S2_PITCH];
+    __shared__ float wsm[36 + 2];
+    const int tid = threadIdx.x;
+    const int tx0 = blockIdx.x * S2_TX, ty0 = blockIdx.y * S2_TY, b = blockIdx.z;
+    const int H = a.H, W = a.W;
+    const size_t img = (size_t)b * H * W;
+    if (tid < 36) wsm[tid] = __ldg(a.w + tid);
+    if (tid >= 64 && tid < 66) wsm[36 + tid - 64] = __ldg(a.bias + tid - 64);
+    for (int i = tid; i < (S2_TY + 2) * S2_PITCH; i += S2_THREADS) {
+        const int y = i / S2_PITCH, x = i - y * S2_PITCH;
+        const int gy = ty0 - 1 + y, gx = tx0 - 1 + x;
+        float2 v = make_float2(0.f, 0.f);
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = ldg2(a.in + (img + (size_t)gy * W + gx) * 2);
+        tile[i] = v;
+    }
+    __syncthreads();
+    const int lx = (tid & 15) * 4, ly = (tid >> 4) * 2;
+    float2 win[4][6];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) win[r][c] = tile[(ly + r) * S2_PITCH + lx + c];
+    float lmax = 0.f;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int gy = ty0 + ly + r;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int gx = tx0 + lx + c;
+            float o0 = wsm[36], o1 = wsm[37];
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+                for (int dx = 0; dx < 3; dx++) {
+                    const float2 v = win[r + dy][c + dx];
+                    const int t = dy * 3 + dx;
+                    o0 = fmaf(v.x, wsm[t], o0);            // W[co=0][ci=0]
+                    o0 = fmaf(v.y, wsm[9 + t], o0);        // W[0][1]
+                    o1 = fmaf(v.x, wsm[18 + t], o1);       // W[1][0]
+                    o1 = fmaf(v.y, wsm[27 + t], o1);       // W[1][1]
+                }
+            if (gy < H && gx < W) {
+                reinterpret_cast<float2*>(a.out)[img + (size_t)gy * W + gx] = make_float2(o0, o1);
+                lmax = fmaxf(lmax, fmaxf(fabsf(o0), fabsf(o1)));
+            }
+        }
+    }
+    publish_amax(a.amax_out, lmax);
+}
+
 }  // namespace hn

@@ -54,6 +54,7 @@ static int fail(int code, const std::string& msg) {
 struct ConvW {      // offsets (in floats) into the packed device blob
     size_t w = 0, b = 0, slope = 0;
     size_t b8 = 0;            // bias zero-padded to 8 entries (tcgen05 kernels always read 8)
+    size_t raw = 0;           // unpacked checkpoint layout [co][ci][3][3] (lean 2->2 state kernel)
     size_t tc = (size_t)-1;   // offset (in halfs) of the tcgen05 B-operand image, C_out = 8 layers only
     size_t tcr = (size_t)-1;  // same for the row-streaming kernel (N = 48 images)
     float tc_inv = 1.f;       // 2^-kw, inverse of the layer's weight block scale
@@ -90,6 +91,7 @@ struct hn_ctx {
     SpecTables spec;
     float* sigma1d = nullptr;
     int rows_L = 1, cols_CW = 1;
+    bool lean_state2 = true;   // dedicated 2->2 conv kernel for conv_state's second layer (both engines)
     bool spec_fast = true;     // use the register-resident N = 256 spectral kernels when they apply
     int spec_chunk = 0;        // samples per rows/cols kernel pair (0: sized to keep a chunk in L2)
     // weights
@@ -225,6 +227,7 @@ static int build_tables(hn_ctx* c) {
     if (const char* ev = getenv("HELMNET_SPEC_CW")) CW = atoi(ev);
     if (const char* ev = getenv("HELMNET_SPEC_CHUNK")) c->spec_chunk = atoi(ev);
     if (const char* ev = getenv("HELMNET_SPEC_FAST")) c->spec_fast = atoi(ev) != 0;
+    if (const char* ev = getenv("HELMNET_LEAN_STATE2")) c->lean_state2 = atoi(ev) != 0;
     // ~56 KB per CTA (four CTAs per SM hide the tile-load latency; measured best at 256: L = 8, CW = 8), but keep
     // column segments >= 32 B unless the line buffers would not fit at all
     while (CW > 4 && spectral_smem_bytes(n, CW, pml) > 56 * 1024) CW >>= 1;
@@ -443,6 +446,7 @@ static void pack_double_conv(Packer& pk, Cursor& cur, ConvW out[2], int cin, int
     out[0].slope = pack_vec(pk, sl, 1);
     out[1].w = pack_conv3(pk, w1, cout, cmid);
     out[1].b = pack_vec(pk, b1, cout);
+    out[1].raw = pack_vec(pk, w1, cout * cmid * 9);
     out[1].slope = out[0].slope;
 #ifdef HN_HAVE_TC
     if (cmid == 8) { pack_tc(pk, w0, cin, out[0]); pack_tcr(pk, w0, cin, out[0]); }
@@ -696,8 +700,21 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
         HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, s1, B, st)));
         Conv3Args t0 = conv_args(c, W.sta[d][0], c->skip[d], c->state[d][cur], c->mid2[d], r, -1, S_SKIP + d, S_STATE + 2 * d + cur);
         HN_TRY((launch_conv3<SRC_A8_B2, 2, true, EPI_STORE>(c, t0, B, st)));
-        Conv3Args t1 = conv_args(c, W.sta[d][1], c->mid2[d], nullptr, c->state[d][nxt], r, S_STATE + 2 * d + nxt);
-        HN_TRY((launch_conv3<SRC_A2, 2, false, EPI_STORE>(c, t1, B, st)));
+        if (c->lean_state2) {
+            State2Args s2;
+            s2.in = c->mid2[d];
+            s2.w = c->wdev + W.sta[d][1].raw;
+            s2.bias = c->wdev + W.sta[d][1].b;
+            s2.out = c->state[d][nxt];
+            s2.amax_out = c->amax + S_STATE + 2 * d + nxt;
+            s2.H = r;
+            s2.W = r;
+            HN_LAUNCH(state2_kernel, dim3((r + S2_TX - 1) / S2_TX, (r + S2_TY - 1) / S2_TY, B), dim3(S2_THREADS), 0, st, s2);
+            c->launches++;
+        } else {
+            Conv3Args t1 = conv_args(c, W.sta[d][1], c->mid2[d], nullptr, c->state[d][nxt], r, S_STATE + 2 * d + nxt);
+            HN_TRY((launch_conv3<SRC_A2, 2, false, EPI_STORE>(c, t1, B, st)));
+        }
         HN_TRY(launch_down(c, d, B, st));
     }
     // bottom
