@@ -27,6 +27,7 @@
 #include "conv_tcr.cuh"
 #include "conv_tcr_down.cuh"
 #include "conv_tcr_up.cuh"
+#include "conv_tcf.cuh"
 #define HN_HAVE_TC 1
 #endif
 
@@ -58,6 +59,7 @@ struct ConvW {      // offsets (in floats) into the packed device blob
     size_t tc = (size_t)-1;   // offset (in halfs) of the tcgen05 B-operand image, C_out = 8 layers only
     size_t tcr = (size_t)-1;  // same for the row-streaming kernel (N = 48 images)
     float tc_inv = 1.f;       // 2^-kw, inverse of the layer's weight block scale
+    float l1 = 0.f, bmax = 0.f;   // max_co sum |W[co]| and max |b|: bound of the layer's output (fused DoubleConv mid scale)
 };
 struct Weights {
     ConvW inc[2], sig[kDepth][2], sta[kDepth][2], down[kDepth], bot[2], up[kDepth], dec[kDepth][2], outc;
@@ -68,7 +70,7 @@ struct hn_ctx {
     double sigma_max = 0, k0 = 1, omega = 1;
     int r[kDepth + 1] = {0};
     int state_len = 0;
-    int engine = 1;            // 1: tcgen05 convolution kernels (default), 0: fp32 CUDA-core kernels
+    int engine = 2;            // 2: tcgen05 kernels with fused DoubleConvs (default), 1: tcgen05 one kernel per conv, 0: fp32 CUDA cores
     // resident fields
     float *wf = nullptr, *res = nullptr, *ksq = nullptr, *src = nullptr, *rx = nullptr;
     float* state[kDepth][2] = {{nullptr}};
@@ -446,12 +448,24 @@ static void pack_double_conv(Packer& pk, Cursor& cur, ConvW out[2], int cin, int
     out[0].slope = pack_vec(pk, sl, 1);
     out[1].w = pack_conv3(pk, w1, cout, cmid);
     out[1].b = pack_vec(pk, b1, cout);
+    {
+        float b8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < cout && i < 8; i++) b8[i] = b1[i];
+        out[1].b8 = pack_vec(pk, b8, 8);
+    }
+    for (int co = 0; co < cmid; co++) {
+        float l1 = 0.f;
+        for (int i = 0; i < cin * 9; i++) l1 += fabsf(w0[(size_t)co * cin * 9 + i]);
+        out[0].l1 = fmaxf(out[0].l1, l1);
+        out[0].bmax = fmaxf(out[0].bmax, fabsf(b0[co]));
+    }
     out[1].raw = pack_vec(pk, w1, cout * cmid * 9);
     out[1].slope = out[0].slope;
 #ifdef HN_HAVE_TC
     if (cmid == 8) { pack_tc(pk, w0, cin, out[0]); pack_tcr(pk, w0, cin, out[0]); }
     if (cmid == 2 && cin == 10) pack_tcr(pk, w0, cin, out[0], 2);   // conv_state.0: C_out = 2 padded to 8 accumulator columns
     if (cout == 8 && cmid == 8) { pack_tc(pk, w1, cmid, out[1]); pack_tcr(pk, w1, cmid, out[1]); }
+    if (cout == 2 && cmid == 2) pack_tcr(pk, w1, cmid, out[1], 2);  // conv_state.2 for the fused DoubleConv kernel
 #endif
 }
 
@@ -470,7 +484,7 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
 #endif
 #ifdef HN_HAVE_TC
     if constexpr (COUT == 2 && SRC == SRC_A8_B2 && EPI == EPI_STORE) {
-        if (c->engine == 1 && a.tcr_bmat != nullptr && a.W >= c->tcr_min_res && (a.H % 2) == 0 && a.amax_in0 != nullptr) {
+        if (c->engine >= 1 && a.tcr_bmat != nullptr && a.W >= c->tcr_min_res && (a.H % 2) == 0 && a.amax_in0 != nullptr) {
             static bool tcr2_attr_done[16] = {false};
             if (!tcr2_attr_done[c->device & 15]) {
                 HN_CUDA(cudaFuncSetAttribute(tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI_STORE2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -494,7 +508,7 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
         }
     }
     if constexpr (COUT == 8) {
-        if (c->engine == 1 && a.tcr_bmat != nullptr && a.W >= c->tcr_min_res && (a.H % 2) == 0 && a.amax_in0 != nullptr) {
+        if (c->engine >= 1 && a.tcr_bmat != nullptr && a.W >= c->tcr_min_res && (a.H % 2) == 0 && a.amax_in0 != nullptr) {
             static bool tcr_attr_done[16] = {false};
             if (!tcr_attr_done[c->device & 15]) {
                 HN_CUDA(cudaFuncSetAttribute(tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -516,7 +530,7 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
             c->launches++;
             return HN_OK;
         }
-        if (c->engine == 1 && a.tc_bmat != nullptr && a.H >= c->tc_min_res && (SRC == SRC_INC || a.amax_in0 != nullptr)) {
+        if (c->engine >= 1 && a.tc_bmat != nullptr && a.H >= c->tc_min_res && (SRC == SRC_INC || a.amax_in0 != nullptr)) {
             static bool tc_attr_done[16] = {false};
             if (!tc_attr_done[c->device & 15]) {
                 HN_CUDA(cudaFuncSetAttribute(tc::conv3x3_tc_kernel<SRC, PRELU, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -589,7 +603,7 @@ static int launch_down(hn_ctx* c, int d, int B, cudaStream_t st) {
     dn.H = r;
     dn.W = r;
 #ifdef HN_HAVE_TC
-    if (c->engine == 1 && W.down[d].tcr != (size_t)-1 && r / 2 >= c->tcd_min_res) {
+    if (c->engine >= 1 && W.down[d].tcr != (size_t)-1 && r / 2 >= c->tcd_min_res) {
         static bool tcd_attr_done[16] = {false};
         if (!tcd_attr_done[c->device & 15]) {
             HN_CUDA(cudaFuncSetAttribute(tcd::down_tcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcd::SMEM_BYTES));
@@ -633,7 +647,7 @@ static int launch_up(hn_ctx* c, int d, int B, cudaStream_t st) {
     up.Hi = r / 2;
     up.Wi = r / 2;
 #ifdef HN_HAVE_TC
-    if (c->engine == 1 && W.up[d].tcr != (size_t)-1 && r / 2 >= c->tcd_min_res && ((r / 2) % 2) == 0) {
+    if (c->engine >= 1 && W.up[d].tcr != (size_t)-1 && r / 2 >= c->tcd_min_res && ((r / 2) % 2) == 0) {
         static bool tcu_attr_done[16] = {false};
         if (!tcu_attr_done[c->device & 15]) {
             HN_CUDA(cudaFuncSetAttribute(tcu::up_tcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcu::SMEM_BYTES));
@@ -666,6 +680,73 @@ static int launch_up(hn_ctx* c, int d, int B, cudaStream_t st) {
     return HN_OK;
 }
 
+#ifdef HN_HAVE_TC
+// Fused DoubleConv (conv_tcf.cuh) when the engine and the level allow it: full-width rows of 128 or 256 pixels.
+// Returns 1 when launched, 0 when the caller has to fall back to two launches, negative on error.
+static int dconv_rows_per_strip(int H, int B, int cap) {
+    int best = 8;
+    long long best_cost = -1;
+    for (int rows = 8; rows <= 128 && rows <= H; rows += 2) {
+        const int spi = (H + rows - 1) / rows;
+        const long long total = (long long)spi * B;
+        const long long g = total < cap ? total : cap;
+        const long long rounds = (total + g - 1) / g;
+        const long long cost = rounds * (rows + 4 + 3);   // + halo rows + pipeline fill/drain per strip
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = rows; }
+    }
+    return best;
+}
+template <int SRC, int NH, int EPI>
+static int launch_dconv_nh(hn_ctx* c, const tcf::Args& t0, int B, cudaStream_t st) {
+    static bool attr_done[16] = {false};
+    if (!attr_done[c->device & 15]) {
+        HN_CUDA(cudaFuncSetAttribute(tcf::dconv_tcf_kernel<SRC, NH, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tcf::smem_bytes(SRC, NH)));
+        attr_done[c->device & 15] = true;
+    }
+    tcf::Args t = t0;
+    const int cap = (NH == 2 ? 1 : 2) * c->num_sms;
+    t.rows = dconv_rows_per_strip(t.H, B, cap);
+    t.spi = (t.H + t.rows - 1) / t.rows;
+    t.total_strips = t.spi * B;
+    const int grid = t.total_strips < cap ? t.total_strips : cap;
+    tcf::dconv_tcf_kernel<SRC, NH, EPI><<<dim3(grid), dim3(tcf::threads(NH)), tcf::smem_bytes(SRC, NH), st>>>(t);
+    c->launches++;
+    return 1;
+}
+template <int SRC, int EPI>
+static int launch_dconv(hn_ctx* c, const ConvW (&w)[2], const float* inA, const float* inB, float* out, int r, int slot_out, int slot_in0,
+                        int slot_in1, int B, cudaStream_t st, const ConvW* outc = nullptr, float* wf = nullptr, float* dwf_out = nullptr) {
+    if (c->engine < 2 || (r != 128 && r != 256) || w[0].tcr == (size_t)-1 || w[1].tcr == (size_t)-1 || !c->tcw) return 0;
+    tcf::Args t;
+    memset(&t, 0, sizeof(t));
+    t.inA = inA; t.inB = inB; t.sigma = c->sigma1d;
+    t.bmat1 = reinterpret_cast<const __half*>(c->tcw + w[0].tcr);
+    t.bmat2 = reinterpret_cast<const __half*>(c->tcw + w[1].tcr);
+    t.bias1 = c->wdev + w[0].b8;
+    t.slope = c->wdev + w[0].slope;
+    t.bias2 = c->wdev + w[1].b8;
+    t.out = out;
+    if (outc) { t.wo = c->wdev + outc->w; t.bo = c->wdev + outc->b; }
+    t.wf = wf; t.dwf_out = dwf_out;
+    t.amax_in0 = c->amax + slot_in0;
+    t.amax_in1 = c->amax + (slot_in1 >= 0 ? slot_in1 : slot_in0);
+    t.amax_out = slot_out >= 0 ? c->amax + slot_out : nullptr;
+    t.error_flag = c->err_flag;
+    t.sigma_max = c->pml > 0 ? (float)c->sigma_max : 0.f;
+    t.w_inv1 = w[0].tc_inv; t.w_inv2 = w[1].tc_inv;
+    t.mid_l1 = w[0].l1; t.mid_bmax = w[0].bmax;
+    t.H = r;
+    if (r == 256) return launch_dconv_nh<SRC, 2, EPI>(c, t, B, st);
+    return launch_dconv_nh<SRC, 1, EPI>(c, t, B, st);
+}
+#define HN_TRY_DCONV(var, expr) \
+    int var = (expr);           \
+    if (var < 0) return var
+#else
+#define HN_TRY_DCONV(var, expr) int var = 0
+#endif
+
 // HybridNet.forward (architectures.py:439-465).  `from_in6`: read the 6-channel input from c->in6 instead of
 // building it from (wf, 1e3*res, sigmas); `raw_out`: store the network output to c->dwf instead of updating wf.
 static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool raw_out) {
@@ -684,20 +765,34 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
     }
     // inc
     {
-        Conv3Args a = conv_args(c, W.inc[0], from_in6 ? c->in6 : c->wf, c->res, c->mid[0], c->r[0], S_IMID, from_in6 ? S_IN6 : S_WF + cur,
-                                from_in6 ? -1 : S_RES + cur);
-        if (from_in6) HN_TRY((launch_conv3<SRC_A8, 8, true, EPI_STORE>(c, a, B, st)));
-        else HN_TRY((launch_conv3<SRC_INC, 8, true, EPI_STORE>(c, a, B, st)));
-        Conv3Args a2 = conv_args(c, W.inc[1], c->mid[0], nullptr, c->x[0], c->r[0], S_X + 0, S_IMID);
-        HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, a2, B, st)));
+        HN_TRY_DCONV(fused, from_in6 ? 0 : (launch_dconv<SRC_INC, EPI_STORE>(c, W.inc, c->wf, c->res, c->x[0], c->r[0], S_X + 0, S_WF + cur,
+                                                                              S_RES + cur, B, st)));
+        if (!fused) {
+            Conv3Args a = conv_args(c, W.inc[0], from_in6 ? c->in6 : c->wf, c->res, c->mid[0], c->r[0], S_IMID, from_in6 ? S_IN6 : S_WF + cur,
+                                    from_in6 ? -1 : S_RES + cur);
+            if (from_in6) HN_TRY((launch_conv3<SRC_A8, 8, true, EPI_STORE>(c, a, B, st)));
+            else HN_TRY((launch_conv3<SRC_INC, 8, true, EPI_STORE>(c, a, B, st)));
+            Conv3Args a2 = conv_args(c, W.inc[1], c->mid[0], nullptr, c->x[0], c->r[0], S_X + 0, S_IMID);
+            HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, a2, B, st)));
+        }
     }
     // encoder
     for (int d = 0; d < kDepth; d++) {
         const int r = c->r[d];
-        Conv3Args s0 = conv_args(c, W.sig[d][0], c->x[d], c->state[d][cur], c->mid[d], r, S_MID + d, S_X + d, S_STATE + 2 * d + cur);
-        HN_TRY((launch_conv3<SRC_A8_B2, 8, true, EPI_STORE>(c, s0, B, st)));
-        Conv3Args s1 = conv_args(c, W.sig[d][1], c->mid[d], nullptr, c->skip[d], r, S_SKIP + d, S_MID + d);
-        HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, s1, B, st)));
+        HN_TRY_DCONV(fsig, (launch_dconv<SRC_A8_B2, EPI_STORE>(c, W.sig[d], c->x[d], c->state[d][cur], c->skip[d], r, S_SKIP + d, S_X + d,
+                                                                S_STATE + 2 * d + cur, B, st)));
+        if (!fsig) {
+            Conv3Args s0 = conv_args(c, W.sig[d][0], c->x[d], c->state[d][cur], c->mid[d], r, S_MID + d, S_X + d, S_STATE + 2 * d + cur);
+            HN_TRY((launch_conv3<SRC_A8_B2, 8, true, EPI_STORE>(c, s0, B, st)));
+            Conv3Args s1 = conv_args(c, W.sig[d][1], c->mid[d], nullptr, c->skip[d], r, S_SKIP + d, S_MID + d);
+            HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, s1, B, st)));
+        }
+        HN_TRY_DCONV(fsta, (launch_dconv<SRC_A8_B2, EPI_STORE2>(c, W.sta[d], c->skip[d], c->state[d][cur], c->state[d][nxt], r,
+                                                                 S_STATE + 2 * d + nxt, S_SKIP + d, S_STATE + 2 * d + cur, B, st)));
+        if (fsta) {
+            HN_TRY(launch_down(c, d, B, st));
+            continue;
+        }
         Conv3Args t0 = conv_args(c, W.sta[d][0], c->skip[d], c->state[d][cur], c->mid2[d], r, -1, S_SKIP + d, S_STATE + 2 * d + cur);
         HN_TRY((launch_conv3<SRC_A8_B2, 2, true, EPI_STORE>(c, t0, B, st)));
         if (c->lean_state2) {
@@ -730,6 +825,15 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
         const int r = c->r[d];
         HN_TRY(launch_up(c, d, B, st));
         // mid[d] is reused as scratch by inc / encoder / decoder; each use has its own amax slot
+        if (d > 0) {
+            HN_TRY_DCONV(fdec, (launch_dconv<SRC_A8_B8, EPI_STORE>(c, W.dec[d], c->upo[d], c->skip[d], c->dec[d], r, S_DEC + d, S_UPO + d,
+                                                                    S_SKIP + d, B, st)));
+            if (fdec) continue;
+        } else {
+            HN_TRY_DCONV(fdec, (launch_dconv<SRC_A8_B8, EPI_OUTC>(c, W.dec[d], c->upo[d], c->skip[d], c->dec[d], r, raw_out ? -1 : S_WF + nxt,
+                                                                   S_UPO + d, S_SKIP + d, B, st, &W.outc, c->wf, raw_out ? c->dwf : nullptr)));
+            if (fdec) continue;
+        }
         Conv3Args d0 = conv_args(c, W.dec[d][0], c->upo[d], c->skip[d], c->mid[d], r, S_DMID + d, S_UPO + d, S_SKIP + d);
         HN_TRY((launch_conv3<SRC_A8_B8, 8, true, EPI_STORE>(c, d0, B, st)));
         Conv3Args d1 = conv_args(c, W.dec[d][1], c->mid[d], nullptr, c->dec[d], r, S_DEC + d, S_DMID + d);
@@ -900,7 +1004,7 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     if (const char* mr = getenv("HELMNET_TC_MIN_RES")) c->tc_min_res = atoi(mr);
     if (const char* mr = getenv("HELMNET_TCR_MIN_RES")) c->tcr_min_res = atoi(mr);
     if (const char* mr = getenv("HELMNET_TCD_MIN_RES")) c->tcd_min_res = atoi(mr);
-    if (const char* en = getenv("HELMNET_ENGINE")) c->engine = atoi(en) == 1 ? 1 : 0;
+    if (const char* en = getenv("HELMNET_ENGINE")) { const int ev = atoi(en); c->engine = ev < 0 ? 0 : ev > 2 ? 2 : ev; }
 #ifndef HN_HAVE_TC
     c->engine = 0;
 #endif
@@ -1294,7 +1398,8 @@ int hn_debug_tensor(hn_ctx* c, const char* name, float* d_out, int batch, void* 
 int hn_set_engine(hn_ctx* c, int engine) {
     if (!c) return fail(HN_ERR_ARG, "ctx is NULL");
 #ifdef HN_HAVE_TC
-    if (engine != 0 && engine != 1) return fail(HN_ERR_ARG, "engine must be 0 (fp32 CUDA cores) or 1 (tcgen05 split-fp16)");
+    if (engine < 0 || engine > 2)
+        return fail(HN_ERR_ARG, "engine must be 0 (fp32 CUDA cores), 1 (tcgen05 split-fp16) or 2 (tcgen05 with fused DoubleConvs)");
 #else
     if (engine != 0) return fail(HN_ERR_ARG, "only engine 0 is available in the emulator build");
 #endif

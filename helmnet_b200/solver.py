@@ -188,7 +188,7 @@ class IterativeSolver(nn.Module):
         self._ctx_max_batch = 0
         self._weights_dirty = True
         self._source_dirty = True
-        self._engine = int(os.environ.get("HELMNET_ENGINE", "1"))   # 1: tcgen05 convolutions (default), 0: fp32 CUDA cores
+        self._engine = int(os.environ.get("HELMNET_ENGINE", "2"))   # 2: tcgen05 + fused DoubleConvs (default), 1: tcgen05, 0: fp32 CUDA cores
         self.register_buffer("sigmas", None)
         self.set_laplacian()
         self.setup_source()
@@ -385,7 +385,8 @@ class IterativeSolver(nn.Module):
         return self._ctx
 
     def set_engine(self, engine: int):
-        """0: fp32 CUDA-core convolutions; 1: tcgen05 split-fp16 tensor-core convolutions (C_out = 8 layers)."""
+        """0: fp32 CUDA-core convolutions; 1: tcgen05 split-fp16 tensor-core convolutions, one kernel per conv;
+        2 (default): the same with every DoubleConv at 128/256-pixel-wide levels fused into one kernel."""
         self._engine = int(engine)
         if self._ctx is not None:
             self.lib.check(self.lib.hn_set_engine(self._ctx, self._engine), "hn_set_engine")

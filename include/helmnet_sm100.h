@@ -118,8 +118,9 @@ int hn_kernels_per_iteration(const hn_ctx* ctx);
 /* Copies an internal activation (NHWC on device) to d_out as NCHW [batch,C,r,r]; name is e.g.
  * "x0", "skip1", "up2", "dec1", "bot", "x3". Returns channel count (>0) or a negative status. */
 int hn_debug_tensor(hn_ctx* ctx, const char* name, float* d_out, int batch, void* stream);
-/* Selects the convolution engine: 0 = fp32 CUDA-core kernels, 1 = tcgen05 split-TF32 kernels for the
- * layers that have one.  Returns the engine now in effect or a negative status. */
+/* Selects the convolution engine: 0 = fp32 CUDA-core kernels, 1 = tcgen05 split-fp16 kernels (one per conv) for the
+ * layers that have one, 2 (default) = the same with each DoubleConv (architectures.py:63-84) of a 128- or 256-pixel
+ * wide level fused into one kernel.  Returns the engine now in effect or a negative status. */
 int hn_set_engine(hn_ctx* ctx, int engine);
 /* Synchronises `stream` and reports device-side faults recorded by the kernels (tcgen05 completion
  * watchdog). Returns HN_OK or HN_ERR_CUDA. */

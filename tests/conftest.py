@@ -46,10 +46,10 @@ def _cuda_solver_base():
     return s
 
 
-@pytest.fixture(params=[0, 1], ids=["simt", "tcgen05"])
+@pytest.fixture(params=[0, 1, 2], ids=["simt", "tcgen05", "tcgen05-fused"])
 def cuda_solver(request, _cuda_solver_base):
     """IterativeSolver on cuda:0 through the product library (fails loudly if it is missing), once per
-    convolution engine: fp32 CUDA cores and tcgen05 split-fp16."""
+    convolution engine: fp32 CUDA cores, tcgen05 split-fp16 (one kernel per conv) and tcgen05 with fused DoubleConvs."""
     _cuda_solver_base.set_engine(request.param)
     yield _cuda_solver_base
     _cuda_solver_base.sync_check()

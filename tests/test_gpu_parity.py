@@ -55,12 +55,14 @@ def test_unet_and_single_step_kat(cuda_solver, gold):
     assert rel_l2(s.get_residual(c("wf"), c("k_sq")), g["residual_of_wf"]) < 1e-6
 
 
-def test_layers_vs_torch_fp32(cuda_solver, f_weights):
-    """Every intermediate activation against plain PyTorch fp32 ops of the same layers (CPU)."""
+@pytest.mark.parametrize("n", [96, 256])
+def test_layers_vs_torch_fp32(cuda_solver, f_weights, n):
+    """Every intermediate activation against plain PyTorch fp32 ops of the same layers (CPU); n = 256 exercises the
+    fused DoubleConv kernels at levels 0 and 1."""
     import torch.nn.functional as F
     import ctypes as C
     from oracle import helmnet_oracle as O
-    s, n, b = cuda_solver, 96, 2
+    s, b = cuda_solver, 2
     s.set_domain_size(n, source_location=[20, 30])
     g = torch.Generator().manual_seed(11)
     inp = torch.randn(b, 6, n, n, generator=g)
@@ -86,7 +88,9 @@ def test_layers_vs_torch_fp32(cuda_solver, f_weights):
         worst[name] = rel_l2(buf, t)
     full, _ = O.unet_forward(w, inp, states)
     worst["out"] = rel_l2(out, full)
-    bad = {k: v for k, v in worst.items() if v > 5e-6}
+    tol = 5e-6 if n <= 96 else 8e-6     # deeper random-input chains at n = 256 accumulate more fp32 rounding (both sides)
+    print(f"engine {s._engine} n {n}:", {k: f"{v:.2e}" for k, v in worst.items()})
+    bad = {k: v for k, v in worst.items() if v > tol}
     assert not bad, f"layers off: {bad}  (all: {worst})"
 
 
