@@ -90,19 +90,9 @@ using tcr::mbar_arrive_expect_tx;
 using tcr::mbar_wait;
 using tcr::tma_load_1d;
 
-// Descriptors are passed as (low word, high word): only the 14-bit start-address field in the low word changes from
-// MMA to MMA, so the issuing warp updates them with one 32-bit (uniform-datapath) add.
-__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(1u));
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
+using tcr::elect_one;
+using tcr::mma_commit;
+using tcr::mma_f16;
 
 // MMAs of ONE operand row: local row k of a strip whose conv has R live output rows; gk = global index of the output
 // row with the same index (dy = 0).  The accumulator of output row y lives in unit 7 - (y & 7), so rows k, k-1, k-2

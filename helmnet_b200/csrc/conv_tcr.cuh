@@ -130,6 +130,27 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+
+// tcgen05.mma, kind::f16, accumulate.  Descriptors are passed as (low word, high word): only the 14-bit start-address
+// field in the low word changes from MMA to MMA.  The MMA-issuing warp runs its loop with warp-UNIFORM control flow
+// and values (whole warp, one elected lane around the asm), so ptxas keeps descriptors in uniform registers and emits
+// back-to-back UTCHMMA; a lone `if (lane == 0)` thread makes it wrap every MMA in an R2UR waterfall loop (~20
+// dependent instructions, ~200 cycles per MMA: the old serial bottleneck of these kernels).
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(1u));
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc::smem_u32(bar)));
+}
+
 template <int SRC, bool PRELU, int EPI>
 __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
     constexpr int G = groups_of(SRC);
@@ -326,19 +347,14 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
         // =============================== MMA issuer ===============================================================
         // input row k (image row y0-1+k) feeds output rows y = k - dy, dy = 0..2; the accumulator of output row y lives
         // in unit 15 - (y & 15), so rows k, k-1, k-2 occupy ascending adjacent units (split in two MMAs at the ring wrap).
-        // This single thread is the serial bottleneck of the pipeline, so everything loop-invariant is hoisted:
-        // descriptors are built once and only their 14-bit start-address field is advanced per row.
-        if (lane == 0) {
-            const uint32_t ring_base = tc::smem_u32(ring), b_base = tc::smem_u32(bsm);
-            uint64_t da0[G][3], db0[G][3];
-#pragma unroll
-            for (int g = 0; g < G; g++)
-#pragma unroll
-                for (int dx = 0; dx < 3; dx++) {
-                    da0[g][dx] = tc::smem_desc(ring_base + (uint32_t)(g * 2 * PS * 16 + dx * 16), PS * 16, 128);
-                    db0[g][dx] = tc::smem_desc(b_base + (uint32_t)((g * 3 + dx) * BROW_BYTES), 128, 256);
-                }
+        // Whole warp, warp-uniform control flow; one elected lane issues (see mma_f16).
+        {
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint64_t da = tc::smem_desc(tc::smem_u32(ring), PS * 16, 128);
+            const uint64_t db = tc::smem_desc(tc::smem_u32(bsm), 128, 256);
+            const uint32_t a_lo0 = (uint32_t)da, a_hi = (uint32_t)(da >> 32), b_lo = (uint32_t)db, b_hi = (uint32_t)(db >> 32);
             constexpr uint32_t kSlot16 = (uint32_t)(slot_bytes(SRC) >> 4);      // operand row pitch in 16-byte units
+            constexpr uint32_t kGroup16 = 2 * PS, kB16 = BROW_BYTES / 16;
             constexpr uint32_t kIdesc48 = kIdescBase | (6u << 17);
             int gj = 0, go = 0;
 #pragma unroll 1
@@ -348,56 +364,54 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
 #pragma unroll 1
                 for (int j = 0; j < gs.NP; j++, gj++) {
                     const int s = gj % SRP;
-                    if (!mbar_wait(smem_full + s, (uint32_t)(gj / SRP) & 1u)) { ok = false; break; }
+                    bool w = mbar_wait(smem_full + s, (uint32_t)(gj / SRP) & 1u);
                     // the accumulators this pair touches first (output rows 2j, 2j+1) must have been drained and zeroed
                     const int gop = (go >> 1) + j;           // global output pair index
-                    if (2 * j < R && !mbar_wait(tmem_empty + (gop & (NPB - 1)), ((uint32_t)(gop / NPB) & 1u) ^ 1u)) { ok = false; break; }
+                    if (2 * j < R) w = mbar_wait(tmem_empty + (gop & (NPB - 1)), ((uint32_t)(gop / NPB) & 1u) ^ 1u) && w;
+                    if (!__all_sync(0xffffffffu, w)) { ok = false; break; }
                     asm volatile("tcgen05.fence::after_thread_sync;");
+                    if (elect_one()) {
 #pragma unroll
-                    for (int t = 0; t < 2; t++) {
-                        const int k = 2 * j + t;
-                        const int gk = go + k;               // global index of output row y = k (dy = 0)
-                        const uint64_t soff = (uint64_t)((uint32_t)(s * 2 + t) * kSlot16);
-                        if (k >= 2 && k < R && (gk & 15) >= 2) {
-                            // common case: three adjacent accumulators (rows k, k-1, k-2), one N = 48 MMA per (group, dx)
-                            const uint32_t d_tmem = tmem_base + (uint32_t)((15 - (gk & 15)) * NC);
-#pragma unroll
-                            for (int g = 0; g < G; g++)
-#pragma unroll
-                                for (int dx = 0; dx < 3; dx++)
-                                    asm volatile(
-                                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-                                        "l"(da0[g][dx] + soff), "l"(db0[g][dx]), "r"(kIdesc48), "r"(1u));
-                        } else {
-                            // strip edges (fewer than three live output rows) and the ring wrap: contiguous sub-ranges of dy
-                            const int dlo = max(0, k - (R - 1)), dhi = min(2, k);
-                            int dy = dlo;
-                            while (dy <= dhi) {
-                                const int u = 15 - ((gk - dy) & 15);
-                                int len = 1;
-                                while (dy + len <= dhi && u + len <= 15) len++;
-                                const uint32_t d_tmem = tmem_base + (uint32_t)(u * NC);
-                                const uint32_t idesc = kIdescBase | ((uint32_t)(2 * len) << 17);          // N = 16 * len
+                        for (int t = 0; t < 2; t++) {
+                            const int k = 2 * j + t;
+                            const int gk = go + k;               // global index of output row y = k (dy = 0)
+                            const uint32_t a_lo = a_lo0 + (uint32_t)(s * 2 + t) * kSlot16;
+                            if (k >= 2 && k < R && (gk & 15) >= 2) {
+                                // common case: three adjacent accumulators (rows k, k-1, k-2), one N = 48 MMA per (group, dx)
+                                const uint32_t d_tmem = tb + (uint32_t)((15 - (gk & 15)) * NC);
 #pragma unroll
                                 for (int g = 0; g < G; g++)
 #pragma unroll
                                     for (int dx = 0; dx < 3; dx++)
-                                        asm volatile(
-                                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-                                            "l"(da0[g][dx] + soff), "l"(db0[g][dx] + (uint64_t)(dy * 32)), "r"(idesc), "r"(1u));
-                                dy += len;
+                                        mma_f16(d_tmem, a_lo + g * kGroup16 + dx, a_hi, b_lo + (uint32_t)(g * 3 + dx) * kB16, b_hi, kIdesc48);
+                            } else {
+                                // strip edges (fewer than three live output rows) and the ring wrap: contiguous sub-ranges of dy
+                                const int dlo = max(0, k - (R - 1)), dhi = min(2, k);
+                                int dy = dlo;
+                                while (dy <= dhi) {
+                                    const int u = 15 - ((gk - dy) & 15);
+                                    int len = 1;
+                                    while (dy + len <= dhi && u + len <= 15) len++;
+                                    const uint32_t d_tmem = tb + (uint32_t)(u * NC);
+                                    const uint32_t idesc = kIdescBase | ((uint32_t)(2 * len) << 17);          // N = 16 * len
+#pragma unroll
+                                    for (int g = 0; g < G; g++)
+#pragma unroll
+                                        for (int dx = 0; dx < 3; dx++)
+                                            mma_f16(d_tmem, a_lo + g * kGroup16 + dx, a_hi, b_lo + (uint32_t)(g * 3 + dx) * kB16 + (uint32_t)(dy * 32),
+                                                    b_hi, idesc);
+                                    dy += len;
+                                }
                             }
                         }
+                        // one commit per pair: frees operand pair slot s AND publishes the accumulators
+                        mma_commit(pair_done + (gj & (NDB - 1)));
                     }
-                    // one commit per pair: frees operand pair slot s AND publishes the accumulators
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc::smem_u32(pair_done + (gj & (NDB - 1)))));
+                    __syncwarp();
                 }
                 go += R;
             }
         }
-        __syncwarp();
     } else {
         // =============================== epilogue ===============================================================
         const int quad = warp & 3;                         // TMEM lane quadrant this warp may access

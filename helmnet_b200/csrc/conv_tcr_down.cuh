@@ -217,14 +217,13 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
         }
     } else if (warp == MMA_WARP) {
         // =============================== MMA issuer ===============================================================
-        if (lane == 0) {
-            const uint32_t ring_base = tc::smem_u32(ring), b_base = tc::smem_u32(bsm);
+        // Whole warp, warp-uniform control flow; one elected lane issues (see tcr::mma_f16).
+        {
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
             // per-kx A descriptor of operand row 0: parity plane (kx+1)&1, start shift (kx+1)>>1 entries
-            uint64_t da0[8];
-#pragma unroll
-            for (int kx = 0; kx < 8; kx++)
-                da0[kx] = tc::smem_desc(ring_base + (uint32_t)(((kx + 1) & 1) * 2 * PS * 16 + ((kx + 1) >> 1) * 16), PS * 16, 128);
-            const uint64_t db0 = tc::smem_desc(b_base, 128, 256);
+            const uint64_t da = tc::smem_desc(tc::smem_u32(ring), PS * 16, 128);
+            const uint64_t db = tc::smem_desc(tc::smem_u32(bsm), 128, 256);
+            const uint32_t a_lo0 = (uint32_t)da, a_hi = (uint32_t)(da >> 32), b_lo = (uint32_t)db, b_hi = (uint32_t)(db >> 32);
             constexpr uint32_t kRow16 = ROW_OP_BYTES >> 4;
             constexpr uint32_t kIdesc64 = kIdescBase | (8u << 17);
             int gj = 0, go = 0;
@@ -235,37 +234,38 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
 #pragma unroll 1
                 for (int j = 0; j < gs.NP; j++, gj++) {
                     const int s = gj % SRP;
-                    if (!mbar_wait(smem_full + s, (uint32_t)(gj / SRP) & 1u)) { ok = false; break; }
+                    bool w = mbar_wait(smem_full + s, (uint32_t)(gj / SRP) & 1u);
                     const int gr = go + j;                    // global index of output row j (first touched by this pair)
-                    if (j < Ro && !mbar_wait(tmem_empty + (gr & (NUB - 1)), ((uint32_t)(gr / NUB) & 1u) ^ 1u)) { ok = false; break; }
+                    if (j < Ro) w = mbar_wait(tmem_empty + (gr & (NUB - 1)), ((uint32_t)(gr / NUB) & 1u) ^ 1u) && w;
+                    if (!__all_sync(0xffffffffu, w)) { ok = false; break; }
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    // live output rows of this pair: j - m, m in [mlo, mhi]
-                    const int mlo = max(0, j - (Ro - 1)), mhi = min(3, j);
-                    int m = mlo;
-                    while (m <= mhi) {
-                        const int u = 15 - ((gr - m) & 15);
-                        int len = 1;
-                        while (m + len <= mhi && u + len <= 15) len++;
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(u * NC);
-                        const uint32_t idesc = (len == 4) ? kIdesc64 : (kIdescBase | ((uint32_t)(2 * len) << 17));
+                    if (tcr::elect_one()) {
+                        // live output rows of this pair: j - m, m in [mlo, mhi]
+                        const int mlo = max(0, j - (Ro - 1)), mhi = min(3, j);
+                        int m = mlo;
+                        while (m <= mhi) {
+                            const int u = 15 - ((gr - m) & 15);
+                            int len = 1;
+                            while (m + len <= mhi && u + len <= 15) len++;
+                            const uint32_t d_tmem = tb + (uint32_t)(u * NC);
+                            const uint32_t idesc = (len == 4) ? kIdesc64 : (kIdescBase | ((uint32_t)(2 * len) << 17));
 #pragma unroll
-                        for (int t = 0; t < 2; t++) {
-                            const uint64_t soff = (uint64_t)((uint32_t)(s * 2 + t) * kRow16);
+                            for (int t = 0; t < 2; t++) {
+                                const uint32_t a_lo = a_lo0 + (uint32_t)(s * 2 + t) * kRow16;
 #pragma unroll
-                            for (int kx = 0; kx < 8; kx++)
-                                asm volatile(
-                                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-                                    "l"(da0[kx] + soff), "l"(db0 + (uint64_t)((t * 8 + kx) * (BIMG_BYTES >> 4) + m * 32)), "r"(idesc), "r"(1u));
+                                for (int kx = 0; kx < 8; kx++)
+                                    tcr::mma_f16(d_tmem, a_lo + (uint32_t)(((kx + 1) & 1) * 2 * PS + ((kx + 1) >> 1)), a_hi,
+                                                 b_lo + (uint32_t)((t * 8 + kx) * (BIMG_BYTES >> 4) + m * 32), b_hi, idesc);
+                            }
+                            m += len;
                         }
-                        m += len;
+                        tcr::mma_commit(pair_done + (gj & (NDB - 1)));
                     }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc::smem_u32(pair_done + (gj & (NDB - 1)))));
+                    __syncwarp();
                 }
                 go += Ro;
             }
         }
-        __syncwarp();
     } else {
         // =============================== epilogue ===============================================================
         const int quad = warp & 3;

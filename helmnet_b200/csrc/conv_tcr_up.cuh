@@ -206,12 +206,12 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
     } else if (warp == MMA_WARP) {
         // =============================== MMA issuer ===============================================================
         // input row k (image row iy0-2+k) feeds output rows oyl = 2k - 7 + ky (strip-local), ky = 0..7, ascending units.
-        if (lane == 0) {
-            const uint32_t ring_base = tc::smem_u32(ring), b_base = tc::smem_u32(bsm);
-            uint64_t da0[5];
-#pragma unroll
-            for (int si = 0; si < 5; si++) da0[si] = tc::smem_desc(ring_base + (uint32_t)(si * 16), PS * 16, 128);   // shift s = si - 2
-            const uint64_t db0 = tc::smem_desc(b_base, 128, 256);
+        // Whole warp, warp-uniform control flow; one elected lane issues (see tcr::mma_f16).
+        {
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint64_t da = tc::smem_desc(tc::smem_u32(ring), PS * 16, 128);     // + si: shift s = si - 2
+            const uint64_t db = tc::smem_desc(tc::smem_u32(bsm), 128, 256);
+            const uint32_t a_lo0 = (uint32_t)da, a_hi = (uint32_t)(da >> 32), b_lo = (uint32_t)db, b_hi = (uint32_t)(db >> 32);
             constexpr uint32_t kRow16 = ROW_OP_BYTES >> 4;
             int gj = 0, go = 0;   // go: output rows finished in previous strips (multiple of 4)
 #pragma unroll 1
@@ -221,38 +221,38 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
 #pragma unroll 1
                 for (int j = 0; j < gs.NP; j++, gj++) {
                     const int s = gj % SRP;
-                    if (!mbar_wait(smem_full + s, (uint32_t)(gj / SRP) & 1u)) { ok = false; break; }
+                    bool w = mbar_wait(smem_full + s, (uint32_t)(gj / SRP) & 1u);
                     // rows first touched by this pair (4j-1 .. 4j+2) reuse the units of rows 16 earlier: epilogue step G done?
                     const int G = (go >> 2) + j - 4;
-                    if (G >= 0 && !mbar_wait(tmem_empty + (G & (NEB - 1)), (uint32_t)(G / NEB) & 1u)) { ok = false; break; }
+                    if (G >= 0) w = mbar_wait(tmem_empty + (G & (NEB - 1)), (uint32_t)(G / NEB) & 1u) && w;
+                    if (!__all_sync(0xffffffffu, w)) { ok = false; break; }
                     asm volatile("tcgen05.fence::after_thread_sync;");
+                    if (tcr::elect_one()) {
 #pragma unroll
-                    for (int t = 0; t < 2; t++) {
-                        const int k = 2 * j + t;
-                        const uint64_t soff = (uint64_t)((uint32_t)(s * 2 + t) * kRow16);
-                        const int klo = max(0, 7 - 2 * k), khi = min(7, Ro + 6 - 2 * k);   // 0 <= 2k-7+ky < Ro
-                        int ky = klo;
-                        while (ky <= khi) {
-                            const int u = (go + 2 * k - 7 + ky) & 15;
-                            int len = 1;
-                            while (ky + len <= khi && u + len <= 15) len++;
-                            const uint32_t d_tmem = tmem_base + (uint32_t)(u * UC);
-                            const uint32_t idesc = kIdescBase | ((uint32_t)(4 * len) << 17);      // N = 32 * len
+                        for (int t = 0; t < 2; t++) {
+                            const int k = 2 * j + t;
+                            const uint32_t a_lo = a_lo0 + (uint32_t)(s * 2 + t) * kRow16;
+                            const int klo = max(0, 7 - 2 * k), khi = min(7, Ro + 6 - 2 * k);   // 0 <= 2k-7+ky < Ro
+                            int ky = klo;
+                            while (ky <= khi) {
+                                const int u = (go + 2 * k - 7 + ky) & 15;
+                                int len = 1;
+                                while (ky + len <= khi && u + len <= 15) len++;
+                                const uint32_t d_tmem = tb + (uint32_t)(u * UC);
+                                const uint32_t idesc = kIdescBase | ((uint32_t)(4 * len) << 17);      // N = 32 * len
 #pragma unroll
-                            for (int si = 0; si < 5; si++)
-                                asm volatile(
-                                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-                                    "l"(da0[si] + soff), "l"(db0 + (uint64_t)(si * (BIMG_BYTES >> 4) + ky * 64)), "r"(idesc), "r"(1u));
-                            ky += len;
+                                for (int si = 0; si < 5; si++)
+                                    tcr::mma_f16(d_tmem, a_lo + (uint32_t)si, a_hi, b_lo + (uint32_t)(si * (BIMG_BYTES >> 4) + ky * 64), b_hi, idesc);
+                                ky += len;
+                            }
                         }
+                        tcr::mma_commit(pair_done + (gj & (NDB - 1)));
                     }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc::smem_u32(pair_done + (gj & (NDB - 1)))));
+                    __syncwarp();
                 }
                 go += Ro;
             }
         }
-        __syncwarp();
     } else {
         // =============================== epilogue ===============================================================
         const int quad = warp & 3;
