@@ -48,8 +48,8 @@ __host__ __device__ constexpr size_t stage_row_bytes(int src, int nh) {
     return (size_t)128 * nh * (src == SRC_INC ? 16 : src == SRC_A8 ? 32 : src == SRC_A8_B2 ? 40 : 64);
 }
 // ring depths in row PAIRS
-__host__ __device__ constexpr int nsp(int src, int nh) { return src == SRC_A8_B8 ? (nh == 2 ? 3 : 2) : (src == SRC_INC ? 4 : 3); }
-__host__ __device__ constexpr int srp1(int src, int nh) { return groups_of(src) == 1 ? 4 : 2; }
+__host__ __device__ constexpr int nsp(int src, int nh) { return src == SRC_A8_B8 ? 2 : (src == SRC_INC ? 4 : 3); }
+__host__ __device__ constexpr int srp1(int src, int nh) { return groups_of(src) == 1 ? 4 : (nh == 2 ? 3 : 2); }
 __host__ __device__ constexpr int srp2(int src, int nh) { return 2; }
 __host__ __device__ constexpr size_t a1_row_bytes(int src, int nh) { return (size_t)groups_of(src) * 2 * psw(nh) * 16; }
 __host__ __device__ constexpr size_t a2_row_bytes(int nh) { return (size_t)2 * psw(nh) * 16; }
@@ -64,12 +64,14 @@ struct Args {
     const float* sigma;
     const __half* bmat1;        // first conv: [groups][3 dx] x 1536 B (pack_tcr)
     const __half* bmat2;        // second conv: [3 dx] x 1536 B
-    const float* bias1;         // [8] zero padded
-    const float* slope;
-    const float* bias2;         // [8] zero padded
+    // small per-layer constants travel as kernel parameters: the epilogues read them straight from the constant bank
+    // (operand form c[0x0][..] of FFMA) instead of re-loading them from shared memory after every tcgen05.wait
+    float bias1[8];             // zero padded
+    float bias2[8];             // zero padded
+    float wo[16];               // 1x1 outc weights [2][8] (EPI_OUTC)
+    float bo[2];
+    float slope;
     float* out;
-    const float* wo;
-    const float* bo;
     float* wf;
     float* dwf_out;
     const unsigned* amax_in0;
@@ -190,7 +192,6 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
     uint64_t* c2_done = a2_full + SRP2;          // [NDB]  tcgen05.commit of conv-2 input (mid) pair
     uint64_t* acc2_empty = c2_done + NDB;        // [NPB]  NET
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + NPB);
-    float* cst = reinterpret_cast<float*>(tmem_slot + 4);   // bias1[8] bias2[8] wo0[8] wo1[8] bo0 bo1 slope
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = a.H;
@@ -220,11 +221,6 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
         uint4* bs2 = reinterpret_cast<uint4*>(b2);
         for (int i = tid; i < G * 3 * BROW_BYTES / 16; i += THREADS) bs1[i] = __ldg(bg1 + i);
         for (int i = tid; i < 3 * BROW_BYTES / 16; i += THREADS) bs2[i] = __ldg(bg2 + i);
-        if (tid < 8) cst[tid] = __ldg(a.bias1 + tid);
-        if (tid >= 32 && tid < 40) cst[8 + tid - 32] = __ldg(a.bias2 + tid - 32);
-        if (EPI == EPI_OUTC && tid >= 64 && tid < 80) cst[16 + tid - 64] = __ldg(a.wo + tid - 64);
-        if (EPI == EPI_OUTC && tid >= 96 && tid < 98) cst[32 + tid - 96] = __ldg(a.bo + tid - 96);
-        if (tid == 100) cst[34] = __ldg(a.slope);
     }
     asm volatile("fence.proxy.async.shared::cta;");
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -258,7 +254,7 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
     const float mult1 = __uint_as_float((uint32_t)(267 - e_in) << 23);                      // x' = x * 2^(140 - e)
     const float scale1 = __uint_as_float((uint32_t)(e_in - 13) << 23) * a.w_inv1;           // 2^(e - 140) * 2^-kw
     const float in_hi = __uint_as_float((uint32_t)(e_in + 1) << 23);                        // >= max |in|
-    const float slope = __ldg(a.slope);
+    const float slope = a.slope;
     const float bound = fmaxf(1.f, fabsf(slope)) * fmaf(in_hi, a.mid_l1, a.mid_bmax);
     const int e_mid = exp_of(bound);
     const float mult2 = __uint_as_float((uint32_t)(267 - e_mid) << 23);
@@ -312,6 +308,7 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
         // =============================== converters: thread <-> image column x = tid ================================
         const int x = tid;
         const float sig_x = SRC == SRC_INC ? __ldg(a.sigma + x) : 0.f;
+        const int sw16 = ((x >> 2) & 1) * 16;
         int gj = 0;
 #pragma unroll 1
         for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
@@ -341,12 +338,16 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
                             g0[2] = 1e3f * r2.x; g0[3] = 1e3f * r2.y;                             // hybridnet.py:566
                             g0[4] = sig_x; g0[5] = __ldg(a.sigma + gy);
                         } else {
-                            const float4 q0 = *reinterpret_cast<const float4*>(src + x * 32), q1 = *reinterpret_cast<const float4*>(src + x * 32 + 16);
+                            // The two 16-byte halves of a pixel are read in an order that alternates every 4 lanes, so the
+                            // 8 lanes of a quarter warp touch 8 distinct 16-byte bank groups (pixel stride is 32 B).
+                            const float4 qa = *reinterpret_cast<const float4*>(src + x * 32 + sw16), qb = *reinterpret_cast<const float4*>(src + x * 32 + (sw16 ^ 16));
+                            const float4 q0 = sw16 ? qb : qa, q1 = sw16 ? qa : qb;
                             g0[0] = q0.x; g0[1] = q0.y; g0[2] = q0.z; g0[3] = q0.w;
                             g0[4] = q1.x; g0[5] = q1.y; g0[6] = q1.z; g0[7] = q1.w;
                             if constexpr (SRC == SRC_A8_B8) {
-                                const float4 s0 = *reinterpret_cast<const float4*>(src + W * 32 + x * 32);
-                                const float4 s1 = *reinterpret_cast<const float4*>(src + W * 32 + x * 32 + 16);
+                                const float4 sa = *reinterpret_cast<const float4*>(src + W * 32 + x * 32 + sw16);
+                                const float4 sb = *reinterpret_cast<const float4*>(src + W * 32 + x * 32 + (sw16 ^ 16));
+                                const float4 s0 = sw16 ? sb : sa, s1 = sw16 ? sa : sb;
                                 g1[0] = s0.x; g1[1] = s0.y; g1[2] = s0.z; g1[3] = s0.w;
                                 g1[4] = s1.x; g1[5] = s1.y; g1[6] = s1.z; g1[7] = s1.w;
                             } else if constexpr (SRC == SRC_A8_B2) {
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
                     const bool inside = gy >= 0 && gy < H;
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
-                        float o = fmaf(fmaf(__uint_as_float(v[t][8 + c]), 1.f / 2048.f, __uint_as_float(v[t][c])), scale1, cst[c]);
+                        float o = fmaf(fmaf(__uint_as_float(v[t][8 + c]), 1.f / 2048.f, __uint_as_float(v[t][c])), scale1, a.bias1[c]);
                         o = o >= 0.f ? o : slope * o;
                         m[c] = inside ? o : 0.f;
                     }
@@ -520,7 +521,7 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
                     float o[8];
 #pragma unroll
                     for (int c = 0; c < 8; c++)
-                        o[c] = fmaf(fmaf(__uint_as_float(v[t][8 + c]), 1.f / 2048.f, __uint_as_float(v[t][c])), scale2, cst[8 + c]);
+                        o[c] = fmaf(fmaf(__uint_as_float(v[t][8 + c]), 1.f / 2048.f, __uint_as_float(v[t][c])), scale2, a.bias2[c]);
                     const size_t pix = img + (size_t)(y0 + ya + t) * W + x;
                     if (EPI == EPI_STORE) {
 #pragma unroll
@@ -532,11 +533,11 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
                         lmax = fmaxf(lmax, fmaxf(fabsf(o[0]), fabsf(o[1])));
                         reinterpret_cast<float2*>(a.out)[pix] = make_float2(o[0], o[1]);
                     } else {
-                        float o0 = cst[32], o1 = cst[33];
+                        float o0 = a.bo[0], o1 = a.bo[1];
 #pragma unroll
                         for (int c = 0; c < 8; c++) {
-                            o0 = fmaf(o[c], cst[16 + c], o0);
-                            o1 = fmaf(o[c], cst[24 + c], o1);
+                            o0 = fmaf(o[c], a.wo[c], o0);
+                            o1 = fmaf(o[c], a.wo[8 + c], o1);
                         }
                         if (a.dwf_out != nullptr) {
                             reinterpret_cast<float2*>(a.dwf_out)[pix] = make_float2(o0, o1);

@@ -98,6 +98,7 @@ struct hn_ctx {
     int spec_chunk = 0;        // samples per rows/cols kernel pair (0: sized to keep a chunk in L2)
     // weights
     float* wdev = nullptr;
+    std::vector<float> whost;   // host copy of the packed fp32 weight blob (offsets of ConvW index both)
     uint16_t* tcw = nullptr;   // fp16 split-weight images for the tcgen05 convolutions
     int* err_flag = nullptr;   // device watchdog flag of the tcgen05 kernels
     unsigned* amax = nullptr;  // [64] running max |x| per activation tensor (publish_amax), feeds the fp16 block scales
@@ -587,6 +588,7 @@ static int set_smem_attrs(hn_ctx* c) {
                                  (int)spectral_smem_bytes(c->n, c->rows_L, c->pml)));
     HN_CUDA(cudaFuncSetAttribute(spectral_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)spectral_smem_bytes(c->n, c->cols_CW, c->pml)));
+    HN_CUDA(cudaFuncSetAttribute(s256::spectral_cols256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s256::COLS_SMEM_BYTES));
     return HN_OK;
 }
 #endif
@@ -723,11 +725,14 @@ static int launch_dconv(hn_ctx* c, const ConvW (&w)[2], const float* inA, const 
     t.inA = inA; t.inB = inB; t.sigma = c->sigma1d;
     t.bmat1 = reinterpret_cast<const __half*>(c->tcw + w[0].tcr);
     t.bmat2 = reinterpret_cast<const __half*>(c->tcw + w[1].tcr);
-    t.bias1 = c->wdev + w[0].b8;
-    t.slope = c->wdev + w[0].slope;
-    t.bias2 = c->wdev + w[1].b8;
+    const float* hw = c->whost.data();
+    for (int i = 0; i < 8; i++) { t.bias1[i] = hw[w[0].b8 + i]; t.bias2[i] = hw[w[1].b8 + i]; }
+    t.slope = hw[w[0].slope];
     t.out = out;
-    if (outc) { t.wo = c->wdev + outc->w; t.bo = c->wdev + outc->b; }
+    if (outc) {
+        for (int i = 0; i < 16; i++) t.wo[i] = hw[outc->w + i];
+        t.bo[0] = hw[outc->b]; t.bo[1] = hw[outc->b + 1];
+    }
     t.wf = wf; t.dwf_out = dwf_out;
     t.amax_in0 = c->amax + slot_in0;
     t.amax_in1 = c->amax + (slot_in1 >= 0 ? slot_in1 : slot_in0);
@@ -888,7 +893,7 @@ static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, co
         a.b0 = b0;
         a.CW = CW;
         if (fast256)
-            HN_LAUNCH(s256::spectral_cols256_kernel, dim3(n / s256::LINES, nb), dim3(s256::THREADS), 0, st, c->spec, a);
+            HN_LAUNCH(s256::spectral_cols256_kernel, dim3(n / s256::LINES, nb), dim3(s256::THREADS), s256::COLS_SMEM_BYTES, st, c->spec, a);
         else
             HN_LAUNCH(spectral_cols_kernel, dim3((n + CW - 1) / CW, nb), dim3(SPEC_THREADS), spectral_smem_bytes(n, CW, c->pml), st,
                       c->spec, a);
@@ -1082,6 +1087,7 @@ int hn_load_weights(hn_ctx* c, const float* host_blob, size_t n_floats) {
     HN_CUDA(cudaDeviceSynchronize());
 #endif
     HN_CUDA(cudaMemcpy(c->wdev, pk.blob.data(), pk.blob.size() * 4, cudaMemcpyHostToDevice));
+    c->whost = pk.blob;   // host copy: small per-layer constants are passed to the tcgen05 kernels as launch parameters
     if (pk.halfs.size() > 458752) return fail(HN_ERR_STATE, "tensor-core weight images exceed the reserved buffer");
     if (!pk.halfs.empty()) HN_CUDA(cudaMemcpy(c->tcw, pk.halfs.data(), pk.halfs.size() * 2, cudaMemcpyHostToDevice));
     c->weights_set = true;
@@ -1473,12 +1479,34 @@ int hn_profile_layer(hn_ctx* c, int which, int reps, float* out_ms, void* stream
                     a.B = B;
                     a.b0 = 0;
                     a.CW = c->cols_CW;
-                    if (fast256) s256::spectral_cols256_kernel<<<dim3(n / s256::LINES, B), dim3(s256::THREADS), 0, st>>>(c->spec, a);
+                    if (fast256) s256::spectral_cols256_kernel<<<dim3(n / s256::LINES, B), dim3(s256::THREADS), s256::COLS_SMEM_BYTES, st>>>(c->spec, a);
                     else
                         spectral_cols_kernel<<<dim3((n + a.CW - 1) / a.CW, B), dim3(SPEC_THREADS), spectral_smem_bytes(n, a.CW, c->pml), st>>>(
                             c->spec, a);
                 }
             } break;
+#ifdef HN_HAVE_TC
+            // fused DoubleConv kernels of level 0 (engine 2); outputs go to the buffers the iteration itself overwrites
+            case 6: {
+                int f = launch_dconv<SRC_INC, EPI_STORE>(c, W.inc, c->wf, c->res, c->x[0], c->r[0], S_X + 0, S_WF + cur, S_RES + cur, B, st);
+                rc = f == 1 ? HN_OK : (f < 0 ? f : fail(HN_ERR_STATE, "fused DoubleConv kernel not available for this level/engine"));
+            } break;
+            case 7: {
+                int f = launch_dconv<SRC_A8_B2, EPI_STORE>(c, W.sig[0], c->x[0], c->state[0][cur], c->skip[0], c->r[0], S_SKIP + 0, S_X + 0,
+                                                           S_STATE + cur, B, st);
+                rc = f == 1 ? HN_OK : (f < 0 ? f : fail(HN_ERR_STATE, "fused DoubleConv kernel not available for this level/engine"));
+            } break;
+            case 8: {
+                int f = launch_dconv<SRC_A8_B2, EPI_STORE2>(c, W.sta[0], c->skip[0], c->state[0][cur], c->state[0][cur ^ 1], c->r[0],
+                                                            S_STATE + (cur ^ 1), S_SKIP + 0, S_STATE + cur, B, st);
+                rc = f == 1 ? HN_OK : (f < 0 ? f : fail(HN_ERR_STATE, "fused DoubleConv kernel not available for this level/engine"));
+            } break;
+            case 9: {   // decode[0] + outc, raw output to the scratch dwf buffer (the wavefield is not touched)
+                int f = launch_dconv<SRC_A8_B8, EPI_OUTC>(c, W.dec[0], c->upo[0], c->skip[0], c->dec[0], c->r[0], -1, S_UPO + 0, S_SKIP + 0, B, st,
+                                                          &W.outc, c->wf, c->dwf);
+                rc = f == 1 ? HN_OK : (f < 0 ? f : fail(HN_ERR_STATE, "fused DoubleConv kernel not available for this level/engine"));
+            } break;
+#endif
             default: rc = fail(HN_ERR_ARG, "unknown kernel id");
         }
     }

@@ -17,13 +17,14 @@ namespace hn {
 namespace s256 {
 
 constexpr int N = 256;
-constexpr int TB = 272;                  // padded transpose buffer per line (pidx(255) = 270)
+constexpr int TB = 274;                  // padded transpose buffer per line (pidx(255) = 270); 274 = 2 mod 16 keeps the
+                                         // column epilogue's reads across the 8 line buffers on distinct banks
 constexpr int LINES = 8;                 // lines per CTA (4 warps x 2)
 constexpr int THREADS = 128;
 constexpr int TILE_P = 9;                // column tile pitch (8 columns + 1 pad)
 
 struct Tab {                             // shared-memory copies of the operator tables
-    float2 tw[N];
+    float2 tw[N];                        // tw[16 j + h] = w256^(h j): lane h reads consecutive entries (no bank conflicts)
     float2 b[N];
     float mk[N];
     float msq[N];
@@ -45,7 +46,7 @@ __device__ __forceinline__ void dft16n(float2 (&a)[16]) {
 __device__ __forceinline__ void fft256(float2 (&a)[16], float2* tb, int h, const float2* tw) {
     dft16n(a);
 #pragma unroll
-    for (int j = 0; j < 16; j++) tb[pidx(16 * h + j)] = (j == 0) ? a[0] : cmul(a[j], tw[h * j]);
+    for (int j = 0; j < 16; j++) tb[pidx(16 * h + j)] = (j == 0) ? a[0] : cmul(a[j], tw[16 * j + h]);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 16; k++) a[k] = tb[pidx(h + 16 * k)];
@@ -86,7 +87,7 @@ __device__ __forceinline__ void axis256(const float2 (&X)[16], float2 (&out)[16]
 
 __device__ __forceinline__ void load_tab(Tab& tab, const SpecTables& t) {
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        tab.tw[i] = __ldg(t.tw + i);
+        tab.tw[i] = __ldg(t.tw + (i & 15) * (i >> 4));
         tab.b[i] = __ldg(t.b + i);
         tab.mk[i] = __ldg(t.mk + i);
         tab.msq[i] = __ldg(t.msq + i);
@@ -115,47 +116,90 @@ __global__ void __launch_bounds__(THREADS) spectral_rows256_kernel(SpecTables t,
     }
 }
 
+// asynchronous global -> shared copies (LDGSTS): the whole working set of a column tile is put in flight at once
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+#ifdef HN_EMU
+    *reinterpret_cast<float2*>(dst) = *reinterpret_cast<const float2*>(src);
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+#ifdef HN_EMU
+    *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef HN_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef HN_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+#endif
+}
+
+struct ColsSmem {
+    Tab tab;
+    float2 tbuf[LINES][TB];
+    float2 tile[N * TILE_P];             // u, 8 columns x 256 rows, pitch 9
+    float2 rxs[N * LINES];               // row part of L u for the same tile, row-major
+    float ksq[N * LINES];
+    float red[THREADS / 32];
+};
+constexpr size_t COLS_SMEM_BYTES = sizeof(ColsSmem);
+
 __global__ void __launch_bounds__(THREADS) spectral_cols256_kernel(SpecTables t, ColsArgs a) {
-    __shared__ Tab tab;
-    __shared__ float2 tbuf[LINES][TB];
-    __shared__ float2 tile[N * TILE_P];
-    __shared__ float red[THREADS / 32];
+    HN_DYN_SMEM(unsigned char, smem_raw);
+    ColsSmem& sh = *reinterpret_cast<ColsSmem*>(smem_raw);
     const int b = blockIdx.y, j0 = blockIdx.x * LINES;
     const size_t img = (size_t)b * N * N;
-    load_tab(tab, t);
+    // group 0: the wavefield tile (needed first); group 1: the epilogue's operands rx and k_sq.  Everything this CTA
+    // reads from HBM is in flight before the first transform starts.
     for (int it = threadIdx.x; it < N * LINES; it += THREADS) {
         const int i = it >> 3, c = it & 7;
-        tile[i * TILE_P + c] = __ldg(a.u + img + (size_t)i * N + j0 + c);
+        cp_async8(&sh.tile[i * TILE_P + c], a.u + img + (size_t)i * N + j0 + c);
     }
-#ifndef HN_EMU
-    // the epilogue's operands (rx, k_sq) are fetched towards L2 now so that their latency hides behind the transforms
-    for (int i = threadIdx.x; i < N; i += THREADS) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rx + img + (size_t)i * N + j0));
-        if (a.ksq != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ksq + img + (size_t)i * N + j0));
+    cp_async_commit();
+    for (int it = threadIdx.x; it < N * LINES / 2; it += THREADS) {   // 16-byte pieces: 4 per 64-byte row segment
+        const int i = it >> 2, q = it & 3;
+        cp_async16(&sh.rxs[i * LINES + 2 * q], a.rx + img + (size_t)i * N + j0 + 2 * q);
     }
-#endif
+    if (a.ksq != nullptr)
+        for (int it = threadIdx.x; it < N * LINES / 4; it += THREADS) {
+            const int i = it >> 1, q = it & 1;
+            cp_async16(&sh.ksq[i * LINES + 4 * q], a.ksq + img + (size_t)i * N + j0 + 4 * q);
+        }
+    cp_async_commit();
+    load_tab(sh.tab, t);
+    cp_async_wait<1>();
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = lane & 15, ll = warp * 2 + (lane >> 4);
     {
         float2 X[16], o[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) X[k] = tile[(h + 16 * k) * TILE_P + ll];
-        fft256(X, tbuf[ll], h, tab.tw);
-        axis256(X, o, tbuf[ll], h, tab, t.a, t.pml);
+        for (int k = 0; k < 16; k++) X[k] = sh.tile[(h + 16 * k) * TILE_P + ll];
+        fft256(X, sh.tbuf[ll], h, sh.tab.tw);
+        axis256(X, o, sh.tbuf[ll], h, sh.tab, t.a, t.pml);
         // the line's transpose buffer is free now: park C(u) there in natural order for the coalesced epilogue
 #pragma unroll
-        for (int j = 0; j < 16; j++) tbuf[ll][pidx(h + 16 * j)] = o[j];
+        for (int j = 0; j < 16; j++) sh.tbuf[ll][pidx(h + 16 * j)] = o[j];
     }
+    cp_async_wait<0>();
     __syncthreads();
     float part = 0.f, lmax = 0.f;
     for (int it = threadIdx.x; it < N * LINES; it += THREADS) {
         const int i = it >> 3, c = it & 7;
         const size_t p = img + (size_t)i * N + j0 + c;
-        float2 r = cadd(__ldg(a.rx + p), tbuf[c][pidx(i)]);
+        float2 r = cadd(sh.rxs[it], sh.tbuf[c][pidx(i)]);
         if (a.ksq != nullptr) {
-            const float kq = __ldg(a.ksq + p);
-            const float2 uu = tile[i * TILE_P + c];
+            const float kq = sh.ksq[it];
+            const float2 uu = sh.tile[i * TILE_P + c];
             r.x = fmaf(kq, uu.x, r.x);
             r.y = fmaf(kq, uu.y, r.y);
         }
@@ -172,11 +216,11 @@ __global__ void __launch_bounds__(THREADS) spectral_cols256_kernel(SpecTables t,
     publish_amax(a.amax_out, lmax);
     if (a.ssq != nullptr) {
         part = warp_sum(part);
-        if (lane == 0) red[warp] = part;
+        if (lane == 0) sh.red[warp] = part;
         __syncthreads();
         if (threadIdx.x == 0) {
             float tot = 0.f;
-            for (int w = 0; w < THREADS / 32; w++) tot += red[w];
+            for (int w = 0; w < THREADS / 32; w++) tot += sh.red[w];
             atomicAdd(a.ssq + (size_t)(*a.slot) * a.B + a.b0 + b, (double)tot);
         }
     }
