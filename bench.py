@@ -290,6 +290,13 @@ def run_ours(args):
                        "definition": "forward() from host sos until max over the batch of test_loss_function RMSE < 1e-3, incl. H2D/D2H"}
             else:
                 ttr = {"reached": False, "iteration_index": None, "ms": None, "iterations_tried": args.residual_iters}
+            # per-sample view (this rank): the reference network itself does not bring every out-of-distribution map below
+            # 1e-3 within the cap (oracle run of the same maps: transient excursions of the residual, then slow decay)
+            first = (hist < 1e-3).float().argmax(dim=0)
+            ok_s = (hist < 1e-3).any(dim=0)
+            ttr["samples_reached_frac"] = float(ok_s.float().mean().item())
+            ttr["median_iteration_index_of_reached"] = int(first[ok_s].median().item()) if bool(ok_s.any()) else None
+            ttr["ms_per_iteration"] = ms_max / K
 
     if rank == 0:
         peaks = load_peaks()
@@ -356,7 +363,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--cpu-iters", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--residual-iters", type=int, default=600, help="iteration cap of the time-to-residual-1e-3 run (0: skip)")
+    ap.add_argument("--residual-iters", type=int, default=1000, help="iteration cap of the time-to-residual-1e-3 run (0: skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

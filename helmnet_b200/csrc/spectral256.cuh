@@ -193,25 +193,34 @@ __global__ void __launch_bounds__(THREADS) spectral_cols256_kernel(SpecTables t,
     cp_async_wait<0>();
     __syncthreads();
     float part = 0.f, lmax = 0.f;
-    for (int it = threadIdx.x; it < N * LINES; it += THREADS) {
-        const int i = it >> 3, c = it & 7;
-        const size_t p = img + (size_t)i * N + j0 + c;
-        float2 r = cadd(sh.rxs[it], sh.tbuf[c][pidx(i)]);
-        if (a.ksq != nullptr) {
-            const float kq = sh.ksq[it];
-            const float2 uu = sh.tile[i * TILE_P + c];
-            r.x = fmaf(kq, uu.x, r.x);
-            r.y = fmaf(kq, uu.y, r.y);
+    constexpr int EPI_CHUNK = 8;          // source loads of a whole chunk are issued before their first use
+    const float2* srcp = a.src != nullptr ? a.src + (a.src_batch > 1 ? img : (size_t)0) + j0 : nullptr;
+#pragma unroll 1
+    for (int it0 = threadIdx.x; it0 < N * LINES; it0 += THREADS * EPI_CHUNK) {
+        float2 sv[EPI_CHUNK];
+#pragma unroll
+        for (int q = 0; q < EPI_CHUNK; q++) {
+            const int it = it0 + q * THREADS;
+            sv[q] = srcp != nullptr ? __ldg(srcp + (size_t)(it >> 3) * N + (it & 7)) : make_float2(0.f, 0.f);
         }
-        if (a.src != nullptr) {
-            const float2 sv = __ldg(a.src + (a.src_batch > 1 ? img : (size_t)0) + (size_t)i * N + j0 + c);
-            r.x -= sv.x;
-            r.y -= sv.y;
+#pragma unroll
+        for (int q = 0; q < EPI_CHUNK; q++) {
+            const int it = it0 + q * THREADS;
+            const int i = it >> 3, c = it & 7;
+            float2 r = cadd(sh.rxs[it], sh.tbuf[c][pidx(i)]);
+            if (a.ksq != nullptr) {
+                const float kq = sh.ksq[it];
+                const float2 uu = sh.tile[i * TILE_P + c];
+                r.x = fmaf(kq, uu.x, r.x);
+                r.y = fmaf(kq, uu.y, r.y);
+            }
+            r.x -= sv[q].x;
+            r.y -= sv[q].y;
+            a.res[img + (size_t)i * N + j0 + c] = r;
+            part = fmaf(r.x, r.x, part);
+            part = fmaf(r.y, r.y, part);
+            lmax = fmaxf(lmax, fmaxf(fabsf(r.x), fabsf(r.y)));
         }
-        a.res[p] = r;
-        part = fmaf(r.x, r.x, part);
-        part = fmaf(r.y, r.y, part);
-        lmax = fmaxf(lmax, fmaxf(fabsf(r.x), fabsf(r.y)));
     }
     publish_amax(a.amax_out, lmax);
     if (a.ssq != nullptr) {
