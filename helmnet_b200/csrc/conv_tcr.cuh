@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
     } else if (warp < PROD_WARPS) {
         // =============================== converters ===============================================================
         const int team = tid / TEAM, p = tid - team * TEAM;     // team t converts row 2j + t; p: position in the row (136 active)
+        const int sw16 = ((p >> 2) & 1) * 16;
         if (p < PS) {
             int gj = 0;
 #pragma unroll 1
@@ -311,12 +312,15 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
                             g0[2] = 1e3f * r2.x; g0[3] = 1e3f * r2.y;                             // hybridnet.py:566
                             g0[4] = __ldg(a.sigma + gx); g0[5] = __ldg(a.sigma + gy);
                         } else {
-                            const float4 q0 = *reinterpret_cast<const float4*>(src + p * 32), q1 = *reinterpret_cast<const float4*>(src + p * 32 + 16);
+                            // halves read in an order that alternates every 4 lanes: conflict-free LDS.128 at a 32-byte stride
+                            const float4 qa = *reinterpret_cast<const float4*>(src + p * 32 + sw16), qb = *reinterpret_cast<const float4*>(src + p * 32 + (sw16 ^ 16));
+                            const float4 q0 = sw16 ? qb : qa, q1 = sw16 ? qa : qb;
                             g0[0] = q0.x; g0[1] = q0.y; g0[2] = q0.z; g0[3] = q0.w;
                             g0[4] = q1.x; g0[5] = q1.y; g0[6] = q1.z; g0[7] = q1.w;
                             if constexpr (SRC == SRC_A8_B8) {
-                                const float4 s0 = *reinterpret_cast<const float4*>(src + ST8 + p * 32);
-                                const float4 s1 = *reinterpret_cast<const float4*>(src + ST8 + p * 32 + 16);
+                                const float4 sa = *reinterpret_cast<const float4*>(src + ST8 + p * 32 + sw16);
+                                const float4 sb = *reinterpret_cast<const float4*>(src + ST8 + p * 32 + (sw16 ^ 16));
+                                const float4 s0 = sw16 ? sb : sa, s1 = sw16 ? sa : sb;
                                 g1[0] = s0.x; g1[1] = s0.y; g1[2] = s0.z; g1[3] = s0.w;
                                 g1[4] = s1.x; g1[5] = s1.y; g1[6] = s1.z; g1[7] = s1.w;
                             } else if constexpr (SRC == SRC_A8_B2) {

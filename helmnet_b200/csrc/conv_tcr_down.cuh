@@ -48,7 +48,7 @@ constexpr size_t SMEM_BYTES = (size_t)NSP * 2 * ROW_ST_BYTES + (size_t)SRP * 2 *
 struct Args {
     const float* in;            // NHWC8 [B][H][W]
     const __half* bmat;         // [2 t][8 kx] x 2048 B canonical K-major images (host packed)
-    const float* bias;          // [8]
+    float bias[8];              // launch parameter: read from the constant bank by the epilogue
     float* out;                 // NHWC8 [B][H/2][W/2]
     const unsigned* amax_in;
     unsigned* amax_out;
@@ -88,7 +88,6 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
     uint64_t* stage_full = tmem_empty + NUB;     // [NSP]
     uint64_t* stage_empty = stage_full + NSP;    // [NSP]  2 x 136
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_empty + NSP);
-    float* cst = reinterpret_cast<float*>(tmem_slot + 4);   // bias[8]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = a.H, W = a.W, Wo = W >> 1;
@@ -112,7 +111,6 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
         const uint4* bg = reinterpret_cast<const uint4*>(a.bmat);
         uint4* bs = reinterpret_cast<uint4*>(bsm);
         for (int i = tid; i < 16 * BIMG_BYTES / 16; i += THREADS) bs[i] = __ldg(bg + i);
-        if (tid < 8) cst[tid] = __ldg(a.bias + tid);
     }
     asm volatile("fence.proxy.async.shared::cta;");
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -173,6 +171,9 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
     } else if (warp < PROD_WARPS) {
         // =============================== converters ===============================================================
         const int team = tid / TEAM, p = tid - team * TEAM;     // p: half-position h; handles pixels xb + 2p and xb + 2p + 1
+        const int rot = (p >> 1) & 3;
+        const bool r1 = (rot & 1) != 0, r2 = (rot & 2) != 0;
+        const int pl_a = r2 ? 2 * PS : 0, pl_b = r2 ? 0 : 2 * PS;
         if (p < PS) {
             int gj = 0;
 #pragma unroll 1
@@ -190,25 +191,30 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
                     for (int c = 0; c < 8; c++) { ge[c] = 0.f; go_[c] = 0.f; }
                     if (!mbar_wait(stage_full + sidx, (uint32_t)(gj / NSP) & 1u)) { ok = false; break; }
                     if (gy >= 0 && gy < H) {
+                        // A thread owns 64 contiguous bytes (even pixel | odd pixel) at a 64-byte stride.  Reading the four
+                        // 16-byte chunks in the rotated order (k + p/2) & 3 makes the 8 lanes of a quarter warp hit 8 distinct
+                        // bank groups; the rotation by 2 is undone for free by swapping the parity planes at the store below,
+                        // the rotation by 1 with one select per value.
                         const uint8_t* src = stage + (size_t)(sidx * 2 + team) * ROW_ST_BYTES + (size_t)p * 64;
-                        if (oke) {
-                            const float4 q0 = *reinterpret_cast<const float4*>(src), q1 = *reinterpret_cast<const float4*>(src + 16);
-                            ge[0] = q0.x; ge[1] = q0.y; ge[2] = q0.z; ge[3] = q0.w; ge[4] = q1.x; ge[5] = q1.y; ge[6] = q1.z; ge[7] = q1.w;
-                        }
-                        if (oko) {
-                            const float4 q0 = *reinterpret_cast<const float4*>(src + 32), q1 = *reinterpret_cast<const float4*>(src + 48);
-                            go_[0] = q0.x; go_[1] = q0.y; go_[2] = q0.z; go_[3] = q0.w; go_[4] = q1.x; go_[5] = q1.y; go_[6] = q1.z; go_[7] = q1.w;
-                        }
+                        const float4 l0 = *reinterpret_cast<const float4*>(src + ((rot + 0) & 3) * 16);
+                        const float4 l1 = *reinterpret_cast<const float4*>(src + ((rot + 1) & 3) * 16);
+                        const float4 l2 = *reinterpret_cast<const float4*>(src + ((rot + 2) & 3) * 16);
+                        const float4 l3 = *reinterpret_cast<const float4*>(src + ((rot + 3) & 3) * 16);
+                        // m_k = chunk (k + 2 * (rot >> 1)) & 3
+                        const float4 m0 = r1 ? l3 : l0, m1 = r1 ? l0 : l1, m2 = r1 ? l1 : l2, m3 = r1 ? l2 : l3;
+                        const bool ok_a = r2 ? oko : oke, ok_b = r2 ? oke : oko;      // (m0, m1) is the odd pixel when r2
+                        if (ok_a) { ge[0] = m0.x; ge[1] = m0.y; ge[2] = m0.z; ge[3] = m0.w; ge[4] = m1.x; ge[5] = m1.y; ge[6] = m1.z; ge[7] = m1.w; }
+                        if (ok_b) { go_[0] = m2.x; go_[1] = m2.y; go_[2] = m2.z; go_[3] = m2.w; go_[4] = m3.x; go_[5] = m3.y; go_[6] = m3.z; go_[7] = m3.w; }
                     }
                     if (gj >= SRP && !mbar_wait(pair_done + ((gj - SRP) & (NDB - 1)), (uint32_t)((gj - SRP) / NDB) & 1u)) { ok = false; break; }
                     uint4* slot = reinterpret_cast<uint4*>(ring + (size_t)(s * 2 + team) * ROW_OP_BYTES);
                     uint4 hi4, lo4;
-                    tc::split8(ge, mult, hi4, lo4);
-                    slot[p] = hi4;
-                    slot[PS + p] = lo4;
+                    tc::split8(ge, mult, hi4, lo4);            // ge: even pixel, or the odd one when r2 (planes swapped)
+                    slot[pl_a + p] = hi4;
+                    slot[pl_a + PS + p] = lo4;
                     tc::split8(go_, mult, hi4, lo4);
-                    slot[2 * PS + p] = hi4;
-                    slot[3 * PS + p] = lo4;
+                    slot[pl_b + p] = hi4;
+                    slot[pl_b + PS + p] = lo4;
                     asm volatile("fence.proxy.async.shared::cta;");
                     mbar_arrive(smem_full + s);
                     mbar_arrive(stage_empty + sidx);
@@ -299,7 +305,7 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
                     float o[8];
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
-                        o[c] = fmaf(fmaf(__uint_as_float(v[8 + c]), 1.f / 2048.f, __uint_as_float(v[c])), out_scale, cst[c]);
+                        o[c] = fmaf(fmaf(__uint_as_float(v[8 + c]), 1.f / 2048.f, __uint_as_float(v[c])), out_scale, a.bias[c]);
                         lmax = fmaxf(lmax, fabsf(o[c]));
                     }
                     float4* dst = reinterpret_cast<float4*>(a.out + (gs.img_out + (size_t)(gs.oy0 + oyl) * Wo + ox) * 8);

@@ -47,7 +47,7 @@ static_assert((size_t)NSP * 2 * ROW_ST_BYTES + (size_t)SRP * 2 * ROW_OP_BYTES + 
 struct Args {
     const float* in;            // NHWC8 [B][Hi][Wi]
     const __half* bmat;         // [5 shifts] x 8192 B canonical K-major images (host packed)
-    const float* bias;          // [8]
+    float bias[8];              // launch parameter: read from the constant bank by the epilogue
     float* out;                 // NHWC8 [B][2Hi][2Wi]
     const unsigned* amax_in;
     unsigned* amax_out;
@@ -87,7 +87,6 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
     uint64_t* stage_full = tmem_empty + NEB;     // [NSP]
     uint64_t* stage_empty = stage_full + NSP;    // [NSP]  2 x 136
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_empty + NSP);
-    float* cst = reinterpret_cast<float*>(tmem_slot + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Hi = a.Hi, Wi = a.Wi, Wo = 2 * Wi;
@@ -111,7 +110,6 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
         const uint4* bg = reinterpret_cast<const uint4*>(a.bmat);
         uint4* bs = reinterpret_cast<uint4*>(bsm);
         for (int i = tid; i < 5 * BIMG_BYTES / 16; i += THREADS) bs[i] = __ldg(bg + i);
-        if (tid < 8) cst[tid] = __ldg(a.bias + tid);
     }
     asm volatile("fence.proxy.async.shared::cta;");
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -171,6 +169,7 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
     } else if (warp < PROD_WARPS) {
         // =============================== converters ===============================================================
         const int team = tid / TEAM, p = tid - team * TEAM;     // p: position, cell x0 - 2 + p
+        const int sw16 = ((p >> 2) & 1) * 16;
         if (p < PS) {
             int gj = 0;
 #pragma unroll 1
@@ -188,7 +187,9 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
                     if (!mbar_wait(stage_full + sidx, (uint32_t)(gj / NSP) & 1u)) { ok = false; break; }
                     if (colok && gy >= 0 && gy < Hi) {
                         const uint8_t* src = stage + (size_t)(sidx * 2 + team) * ROW_ST_BYTES + (size_t)p * 32;
-                        const float4 q0 = *reinterpret_cast<const float4*>(src), q1 = *reinterpret_cast<const float4*>(src + 16);
+                        // halves read in an order that alternates every 4 lanes: conflict-free LDS.128 at a 32-byte stride
+                        const float4 qa = *reinterpret_cast<const float4*>(src + sw16), qb = *reinterpret_cast<const float4*>(src + (sw16 ^ 16));
+                        const float4 q0 = sw16 ? qb : qa, q1 = sw16 ? qa : qb;
                         g0[0] = q0.x; g0[1] = q0.y; g0[2] = q0.z; g0[3] = q0.w; g0[4] = q1.x; g0[5] = q1.y; g0[6] = q1.z; g0[7] = q1.w;
                     }
                     if (gj >= SRP && !mbar_wait(pair_done + ((gj - SRP) & (NDB - 1)), (uint32_t)((gj - SRP) / NDB) & 1u)) { ok = false; break; }
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
                             float o[8];
 #pragma unroll
                             for (int c = 0; c < 8; c++) {
-                                o[c] = fmaf(fmaf(__uint_as_float(v[px * 16 + 8 + c]), 1.f / 2048.f, __uint_as_float(v[px * 16 + c])), out_scale, cst[c]);
+                                o[c] = fmaf(fmaf(__uint_as_float(v[px * 16 + 8 + c]), 1.f / 2048.f, __uint_as_float(v[px * 16 + c])), out_scale, a.bias[c]);
                                 lmax = fmaxf(lmax, fabsf(o[c]));
                             }
                             dst[2 * px] = make_float4(o[0], o[1], o[2], o[3]);

@@ -614,7 +614,7 @@ static int launch_down(hn_ctx* c, int d, int B, cudaStream_t st) {
         tcd::Args t;
         t.in = c->skip[d];
         t.bmat = reinterpret_cast<const __half*>(c->tcw + W.down[d].tcr);
-        t.bias = c->wdev + W.down[d].b;
+        for (int i = 0; i < 8; i++) t.bias[i] = c->whost[W.down[d].b + i];
         t.out = c->x[d + 1];
         t.amax_in = c->amax + S_SKIP + d;
         t.amax_out = c->amax + S_X + d + 1;
@@ -658,7 +658,7 @@ static int launch_up(hn_ctx* c, int d, int B, cudaStream_t st) {
         tcu::Args t;
         t.in = up.in;
         t.bmat = reinterpret_cast<const __half*>(c->tcw + W.up[d].tcr);
-        t.bias = up.bias;
+        for (int i = 0; i < 8; i++) t.bias[i] = c->whost[W.up[d].b + i];
         t.out = up.out;
         t.amax_in = c->amax + ((d == kDepth - 1) ? S_BOT : S_DEC + d + 1);
         t.amax_out = up.amax_out;
