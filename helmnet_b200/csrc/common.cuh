@@ -63,6 +63,18 @@ __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
+// One NHWC8 pixel (32 bytes, 32-byte aligned) as a single 256-bit store: every store instruction fills whole 32-byte
+// sectors (two 128-bit stores at a 32-byte thread stride each write half sectors, twice the L2 write requests).
+__device__ __forceinline__ void st_nhwc8(float* dst, const float (&o)[8]) {
+#ifdef HN_EMU
+    reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+#else
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]),
+                 "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+#endif
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -293,8 +293,7 @@ __global__ void __launch_bounds__(THREADS, (groups_of(SRC) == 1) ? 4 : 2) conv3x
             const size_t pix = img + (size_t)gy * W + gx;
             if (EPI == EPI_STORE) {
                 float4* dst = reinterpret_cast<float4*>(a.out + pix * 8);
-                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+                st_nhwc8(reinterpret_cast<float*>(dst), o);
             } else {
                 float o0 = bo0, o1 = bo1;
 #pragma unroll

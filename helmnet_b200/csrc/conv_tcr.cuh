@@ -473,8 +473,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
 #pragma unroll
                             for (int c = 0; c < 8; c++) lmax = fmaxf(lmax, fabsf(o[c]));
                             float4* dst = reinterpret_cast<float4*>(a.out + pix * 8);
-                            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-                            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+                            st_nhwc8(reinterpret_cast<float*>(dst), o);
                         } else if (EPI == EPI_STORE2) {
                             lmax = fmaxf(lmax, fmaxf(fabsf(o[0]), fabsf(o[1])));
                             reinterpret_cast<float2*>(a.out)[pix] = make_float2(o[0], o[1]);

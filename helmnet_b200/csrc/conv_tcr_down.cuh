@@ -309,8 +309,7 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
                         lmax = fmaxf(lmax, fabsf(o[c]));
                     }
                     float4* dst = reinterpret_cast<float4*>(a.out + (gs.img_out + (size_t)(gs.oy0 + oyl) * Wo + ox) * 8);
-                    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-                    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+                    st_nhwc8(reinterpret_cast<float*>(dst), o);
                 }
             }
             gj += gs.NP;

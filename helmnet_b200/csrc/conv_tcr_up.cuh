@@ -296,8 +296,7 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
                                 o[c] = fmaf(fmaf(__uint_as_float(v[px * 16 + 8 + c]), 1.f / 2048.f, __uint_as_float(v[px * 16 + c])), out_scale, a.bias[c]);
                                 lmax = fmaxf(lmax, fabsf(o[c]));
                             }
-                            dst[2 * px] = make_float4(o[0], o[1], o[2], o[3]);
-                            dst[2 * px + 1] = make_float4(o[4], o[5], o[6], o[7]);
+                            st_nhwc8(reinterpret_cast<float*>(dst + 2 * px), o);
                         }
                     }
                 }
