@@ -22,6 +22,7 @@
 #include "layout.cuh"
 #include "spectral.cuh"
 #include "spectral256.cuh"
+#include "spectral512.cuh"
 #ifndef HN_EMU
 #include "conv_tc.cuh"
 #include "conv_tcr.cuh"
@@ -589,6 +590,8 @@ static int set_smem_attrs(hn_ctx* c) {
     HN_CUDA(cudaFuncSetAttribute(spectral_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)spectral_smem_bytes(c->n, c->cols_CW, c->pml)));
     HN_CUDA(cudaFuncSetAttribute(s256::spectral_cols256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s256::COLS_SMEM_BYTES));
+    HN_CUDA(cudaFuncSetAttribute(s512::spectral_rows512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s512::ROWS_SMEM_BYTES));
+    HN_CUDA(cudaFuncSetAttribute(s512::spectral_cols512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s512::COLS_SMEM_BYTES));
     return HN_OK;
 }
 #endif
@@ -873,9 +876,14 @@ static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, co
         const size_t off = (size_t)b0 * n * n;
         const int total_rows = nb * n;
         const bool fast256 = (n == 256 && c->pml <= 16 && c->spec_fast);
+        const bool fast512 = (n == 512 && c->pml <= 16 && c->spec_fast);
         if (fast256)
             HN_LAUNCH(s256::spectral_rows256_kernel, dim3((total_rows + s256::LINES - 1) / s256::LINES), dim3(s256::THREADS), 0, st,
                       c->spec, reinterpret_cast<const float2*>(u) + off, reinterpret_cast<float2*>(c->rx) + off, total_rows);
+        else if (fast512)
+            HN_LAUNCH(s512::spectral_rows512_kernel, dim3((total_rows + s512::LINES - 1) / s512::LINES), dim3(s512::THREADS),
+                      s512::ROWS_SMEM_BYTES, st, c->spec, reinterpret_cast<const float2*>(u) + off,
+                      reinterpret_cast<float2*>(c->rx) + off, total_rows);
         else
             HN_LAUNCH(spectral_rows_kernel, dim3((total_rows + L - 1) / L), dim3(SPEC_THREADS), spectral_smem_bytes(n, L, c->pml), st,
                       c->spec, reinterpret_cast<const float2*>(u) + off, reinterpret_cast<float2*>(c->rx) + off, total_rows, L);
@@ -894,6 +902,8 @@ static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, co
         a.CW = CW;
         if (fast256)
             HN_LAUNCH(s256::spectral_cols256_kernel, dim3(n / s256::LINES, nb), dim3(s256::THREADS), s256::COLS_SMEM_BYTES, st, c->spec, a);
+        else if (fast512)
+            HN_LAUNCH(s512::spectral_cols512_kernel, dim3(n / s512::LINES, nb), dim3(s512::THREADS), s512::COLS_SMEM_BYTES, st, c->spec, a);
         else
             HN_LAUNCH(spectral_cols_kernel, dim3((n + CW - 1) / CW, nb), dim3(SPEC_THREADS), spectral_smem_bytes(n, CW, c->pml), st,
                       c->spec, a);
@@ -1456,9 +1466,14 @@ int hn_profile_layer(hn_ctx* c, int which, int reps, float* out_ms, void* stream
             case 5: {
                 const int n = c->n;
                 const bool fast256 = (n == 256 && c->pml <= 16 && c->spec_fast);
+                const bool fast512 = (n == 512 && c->pml <= 16 && c->spec_fast);
                 if (which == 4) {
                     const int total_rows = B * n;
-                    if (fast256)
+                    if (fast512)
+                        s512::spectral_rows512_kernel<<<dim3((total_rows + s512::LINES - 1) / s512::LINES), dim3(s512::THREADS),
+                                                        s512::ROWS_SMEM_BYTES, st>>>(
+                            c->spec, reinterpret_cast<const float2*>(c->wf), reinterpret_cast<float2*>(c->rx), total_rows);
+                    else if (fast256)
                         s256::spectral_rows256_kernel<<<dim3((total_rows + s256::LINES - 1) / s256::LINES), dim3(s256::THREADS), 0, st>>>(
                             c->spec, reinterpret_cast<const float2*>(c->wf), reinterpret_cast<float2*>(c->rx), total_rows);
                     else
@@ -1480,6 +1495,8 @@ int hn_profile_layer(hn_ctx* c, int which, int reps, float* out_ms, void* stream
                     a.b0 = 0;
                     a.CW = c->cols_CW;
                     if (fast256) s256::spectral_cols256_kernel<<<dim3(n / s256::LINES, B), dim3(s256::THREADS), s256::COLS_SMEM_BYTES, st>>>(c->spec, a);
+                    else if (fast512)
+                        s512::spectral_cols512_kernel<<<dim3(n / s512::LINES, B), dim3(s512::THREADS), s512::COLS_SMEM_BYTES, st>>>(c->spec, a);
                     else
                         spectral_cols_kernel<<<dim3((n + a.CW - 1) / a.CW, B), dim3(SPEC_THREADS), spectral_smem_bytes(n, a.CW, c->pml), st>>>(
                             c->spec, a);

@@ -46,6 +46,29 @@ def test_laplacian_n256_register_fft(emu_solver, pml):
         emu_solver.hparams.PMLsize = old
 
 
+@pytest.mark.parametrize("pml", [8, 13])
+def test_laplacian_and_residual_n512_register_fft(emu_solver, pml):
+    """N = 512: one warp per line, two 256-point register transforms + a radix-2 butterfly across the half-warps
+    (spectral512.cuh); pml 13 has threads owning strip samples of both parities."""
+    from oracle import helmnet_oracle as O
+    old = emu_solver.hparams.PMLsize
+    emu_solver.hparams.PMLsize = pml
+    try:
+        emu_solver.set_domain_size(512, source_location=[450, 256])
+        gen = torch.Generator().manual_seed(11)
+        u = torch.randn(1, 512, 512, 2, generator=gen)
+        op = O.make_operator(512, pml, 2.0, 1.0)
+        assert rel_l2(emu_solver.Lap(u), O.laplacian(u, op)) < 1e-6
+        # residual r = L u + k_sq u - source through the fused column epilogue
+        wf = torch.randn(1, 2, 512, 512, generator=gen)
+        k_sq = 1.0 + torch.rand(1, 1, 512, 512, generator=gen)
+        lu = O.laplacian(wf.permute(0, 2, 3, 1).contiguous(), op).permute(0, 3, 1, 2)
+        ref = lu + k_sq * wf - emu_solver.source
+        assert rel_l2(emu_solver.get_residual(wf, k_sq), ref) < 1e-6
+    finally:
+        emu_solver.hparams.PMLsize = old
+
+
 def test_unet_and_single_step(emu_solver, gold):
     g = gold("unet_step_n32.npz")
     s = emu_solver
