@@ -219,8 +219,8 @@ def run_ours(args):
             (6, "dconv_tcf_kernel<INC,STORE> (inc 6->8->8, level 0; reads wf 8 + res 8)", 8 + 8 + 32),
             (2, "down_tcr_kernel (enc[0].down, level 0 -> 1)", 32 + 8),
             (3, "up_tcr_kernel (up[0], level 1 -> 0)", 8 + 32),
-            (4, f"spectral_rows{n}_kernel" if n in (256, 512) else "spectral_rows_kernel", 8 + 8),
-            (5, f"spectral_cols{n}_kernel" if n in (256, 512) else "spectral_cols_kernel", 8 + 8 + 4 + 8),
+            (4, f"spectral_rows{n}_kernel" if n in (256, 512, 1024) else "spectral_rows_kernel", 8 + 8),
+            (5, f"spectral_cols{n}_kernel" if n in (256, 512, 1024) else "spectral_cols_kernel", 8 + 8 + 4 + 8),
         ]
     else:
         kernel_table = [
@@ -228,8 +228,8 @@ def run_ours(args):
             (1, "conv3x3_tcr_kernel<SRC_A8_B8> (decode[0] conv #1, 16->8, level 0)", 64 + 32),
             (2, "down_tcr_kernel (enc[0].down, level 0 -> 1)", 32 + 8),
             (3, "up_tcr_kernel (up[0], level 1 -> 0)", 8 + 32),
-            (4, f"spectral_rows{n}_kernel" if n in (256, 512) else "spectral_rows_kernel", 8 + 8),
-            (5, f"spectral_cols{n}_kernel" if n in (256, 512) else "spectral_cols_kernel", 8 + 8 + 4 + 8),
+            (4, f"spectral_rows{n}_kernel" if n in (256, 512, 1024) else "spectral_rows_kernel", 8 + 8),
+            (5, f"spectral_cols{n}_kernel" if n in (256, 512, 1024) else "spectral_cols_kernel", 8 + 8 + 4 + 8),
         ]
     kern_ms = {}
     one = C.c_float()

@@ -23,6 +23,7 @@
 #include "spectral.cuh"
 #include "spectral256.cuh"
 #include "spectral512.cuh"
+#include "spectral1024.cuh"
 #ifndef HN_EMU
 #include "conv_tc.cuh"
 #include "conv_tcr.cuh"
@@ -592,6 +593,8 @@ static int set_smem_attrs(hn_ctx* c) {
     HN_CUDA(cudaFuncSetAttribute(s256::spectral_cols256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s256::COLS_SMEM_BYTES));
     HN_CUDA(cudaFuncSetAttribute(s512::spectral_rows512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s512::ROWS_SMEM_BYTES));
     HN_CUDA(cudaFuncSetAttribute(s512::spectral_cols512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s512::COLS_SMEM_BYTES));
+    HN_CUDA(cudaFuncSetAttribute(s1024::spectral_rows1024_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1024::ROWS_SMEM_BYTES));
+    HN_CUDA(cudaFuncSetAttribute(s1024::spectral_cols1024_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1024::COLS_SMEM_BYTES));
     return HN_OK;
 }
 #endif
@@ -877,12 +880,17 @@ static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, co
         const int total_rows = nb * n;
         const bool fast256 = (n == 256 && c->pml <= 16 && c->spec_fast);
         const bool fast512 = (n == 512 && c->pml <= 16 && c->spec_fast);
+        const bool fast1024 = (n == 1024 && c->pml <= 16 && c->spec_fast);
         if (fast256)
             HN_LAUNCH(s256::spectral_rows256_kernel, dim3((total_rows + s256::LINES - 1) / s256::LINES), dim3(s256::THREADS), 0, st,
                       c->spec, reinterpret_cast<const float2*>(u) + off, reinterpret_cast<float2*>(c->rx) + off, total_rows);
         else if (fast512)
             HN_LAUNCH(s512::spectral_rows512_kernel, dim3((total_rows + s512::LINES - 1) / s512::LINES), dim3(s512::THREADS),
                       s512::ROWS_SMEM_BYTES, st, c->spec, reinterpret_cast<const float2*>(u) + off,
+                      reinterpret_cast<float2*>(c->rx) + off, total_rows);
+        else if (fast1024)
+            HN_LAUNCH(s1024::spectral_rows1024_kernel, dim3((total_rows + s1024::ROWS_LINES - 1) / s1024::ROWS_LINES),
+                      dim3(s1024::ROWS_THREADS), s1024::ROWS_SMEM_BYTES, st, c->spec, reinterpret_cast<const float2*>(u) + off,
                       reinterpret_cast<float2*>(c->rx) + off, total_rows);
         else
             HN_LAUNCH(spectral_rows_kernel, dim3((total_rows + L - 1) / L), dim3(SPEC_THREADS), spectral_smem_bytes(n, L, c->pml), st,
@@ -904,6 +912,9 @@ static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, co
             HN_LAUNCH(s256::spectral_cols256_kernel, dim3(n / s256::LINES, nb), dim3(s256::THREADS), s256::COLS_SMEM_BYTES, st, c->spec, a);
         else if (fast512)
             HN_LAUNCH(s512::spectral_cols512_kernel, dim3(n / s512::LINES, nb), dim3(s512::THREADS), s512::COLS_SMEM_BYTES, st, c->spec, a);
+        else if (fast1024)
+            HN_LAUNCH(s1024::spectral_cols1024_kernel, dim3(n / s1024::COLS, nb), dim3(s1024::COLS_THREADS), s1024::COLS_SMEM_BYTES, st,
+                      c->spec, a);
         else
             HN_LAUNCH(spectral_cols_kernel, dim3((n + CW - 1) / CW, nb), dim3(SPEC_THREADS), spectral_smem_bytes(n, CW, c->pml), st,
                       c->spec, a);
@@ -1469,7 +1480,11 @@ int hn_profile_layer(hn_ctx* c, int which, int reps, float* out_ms, void* stream
                 const bool fast512 = (n == 512 && c->pml <= 16 && c->spec_fast);
                 if (which == 4) {
                     const int total_rows = B * n;
-                    if (fast512)
+                    if (n == 1024 && c->pml <= 16 && c->spec_fast)
+                        s1024::spectral_rows1024_kernel<<<dim3((total_rows + s1024::ROWS_LINES - 1) / s1024::ROWS_LINES),
+                                                          dim3(s1024::ROWS_THREADS), s1024::ROWS_SMEM_BYTES, st>>>(
+                            c->spec, reinterpret_cast<const float2*>(c->wf), reinterpret_cast<float2*>(c->rx), total_rows);
+                    else if (fast512)
                         s512::spectral_rows512_kernel<<<dim3((total_rows + s512::LINES - 1) / s512::LINES), dim3(s512::THREADS),
                                                         s512::ROWS_SMEM_BYTES, st>>>(
                             c->spec, reinterpret_cast<const float2*>(c->wf), reinterpret_cast<float2*>(c->rx), total_rows);
@@ -1497,6 +1512,9 @@ int hn_profile_layer(hn_ctx* c, int which, int reps, float* out_ms, void* stream
                     if (fast256) s256::spectral_cols256_kernel<<<dim3(n / s256::LINES, B), dim3(s256::THREADS), s256::COLS_SMEM_BYTES, st>>>(c->spec, a);
                     else if (fast512)
                         s512::spectral_cols512_kernel<<<dim3(n / s512::LINES, B), dim3(s512::THREADS), s512::COLS_SMEM_BYTES, st>>>(c->spec, a);
+                    else if (n == 1024 && c->pml <= 16 && c->spec_fast)
+                        s1024::spectral_cols1024_kernel<<<dim3(n / s1024::COLS, B), dim3(s1024::COLS_THREADS), s1024::COLS_SMEM_BYTES, st>>>(
+                            c->spec, a);
                     else
                         spectral_cols_kernel<<<dim3((n + a.CW - 1) / a.CW, B), dim3(SPEC_THREADS), spectral_smem_bytes(n, a.CW, c->pml), st>>>(
                             c->spec, a);

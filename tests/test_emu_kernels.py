@@ -69,6 +69,20 @@ def test_laplacian_and_residual_n512_register_fft(emu_solver, pml):
         emu_solver.hparams.PMLsize = old
 
 
+def test_laplacian_and_residual_n1024_register_fft(emu_solver):
+    """N = 1024: two warps per line, radix-2 across the warps around the 512-point warp transforms (spectral1024.cuh)."""
+    from oracle import helmnet_oracle as O
+    emu_solver.set_domain_size(1024, source_location=[60, 512])
+    gen = torch.Generator().manual_seed(13)
+    u = torch.randn(1, 1024, 1024, 2, generator=gen)
+    op = O.make_operator(1024, 8, 2.0, 1.0)
+    assert rel_l2(emu_solver.Lap(u), O.laplacian(u, op)) < 1e-6
+    wf = torch.randn(1, 2, 1024, 1024, generator=gen)
+    k_sq = 1.0 + torch.rand(1, 1, 1024, 1024, generator=gen)
+    lu = O.laplacian(wf.permute(0, 2, 3, 1).contiguous(), op).permute(0, 3, 1, 2)
+    assert rel_l2(emu_solver.get_residual(wf, k_sq), lu + k_sq * wf - emu_solver.source) < 1e-6
+
+
 def test_unet_and_single_step(emu_solver, gold):
     g = gold("unet_step_n32.npz")
     s = emu_solver
