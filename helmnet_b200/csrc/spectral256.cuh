@@ -8,8 +8,9 @@
 // transforms, so the three transforms of a line (u^ ; first derivative for the PML strips ; second derivative) need
 // no block-wide barrier and only three shared-memory transposes.
 //   rows kernel: global -> registers directly (16 lanes read 128 contiguous bytes), results registers -> global.
-//   cols kernel: 8 columns of one sample staged through a padded shared-memory tile for coalesced 64-byte segments,
-//                fused with  r = rx + C(u) + k_sq u - source,  sum r^2  and  max |r|.
+//   cols kernel: 8 columns of one sample staged with cp.async through a padded shared-memory tile (coalesced 64-byte
+//                segments), fused with  r = rx + C(u) + k_sq u - source,  sum r^2  and  max |r|; the epilogue's operands
+//                are prefetched to L2 at kernel start and loaded 8 points at a time before their first use.
 #pragma once
 #include "spectral.cuh"
 
@@ -143,12 +144,10 @@ __device__ __forceinline__ void cp_async_wait() {
 #endif
 }
 
-struct ColsSmem {
+struct ColsSmem {                        // 42 KB -> 5 CTAs per SM (staging rx and k_sq as well: 67 KB, 3 CTAs, measured slower)
     Tab tab;
     float2 tbuf[LINES][TB];
-    float2 tile[N * TILE_P];             // u, 8 columns x 256 rows, pitch 9
-    float2 rxs[N * LINES];               // row part of L u for the same tile, row-major
-    float ksq[N * LINES];
+    float2 tile[N * TILE_P];
     float red[THREADS / 32];
 };
 constexpr size_t COLS_SMEM_BYTES = sizeof(ColsSmem);
@@ -158,25 +157,19 @@ __global__ void __launch_bounds__(THREADS) spectral_cols256_kernel(SpecTables t,
     ColsSmem& sh = *reinterpret_cast<ColsSmem*>(smem_raw);
     const int b = blockIdx.y, j0 = blockIdx.x * LINES;
     const size_t img = (size_t)b * N * N;
-    // group 0: the wavefield tile (needed first); group 1: the epilogue's operands rx and k_sq.  Everything this CTA
-    // reads from HBM is in flight before the first transform starts.
     for (int it = threadIdx.x; it < N * LINES; it += THREADS) {
         const int i = it >> 3, c = it & 7;
         cp_async8(&sh.tile[i * TILE_P + c], a.u + img + (size_t)i * N + j0 + c);
     }
     cp_async_commit();
-    for (int it = threadIdx.x; it < N * LINES / 2; it += THREADS) {   // 16-byte pieces: 4 per 64-byte row segment
-        const int i = it >> 2, q = it & 3;
-        cp_async16(&sh.rxs[i * LINES + 2 * q], a.rx + img + (size_t)i * N + j0 + 2 * q);
+#ifndef HN_EMU
+    for (int i = threadIdx.x; i < N; i += THREADS) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rx + img + (size_t)i * N + j0));
+        if (a.ksq != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ksq + img + (size_t)i * N + j0));
     }
-    if (a.ksq != nullptr)
-        for (int it = threadIdx.x; it < N * LINES / 4; it += THREADS) {
-            const int i = it >> 1, q = it & 1;
-            cp_async16(&sh.ksq[i * LINES + 4 * q], a.ksq + img + (size_t)i * N + j0 + 4 * q);
-        }
-    cp_async_commit();
+#endif
     load_tab(sh.tab, t);
-    cp_async_wait<1>();
+    cp_async_wait<0>();
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = lane & 15, ll = warp * 2 + (lane >> 4);
@@ -186,34 +179,33 @@ __global__ void __launch_bounds__(THREADS) spectral_cols256_kernel(SpecTables t,
         for (int k = 0; k < 16; k++) X[k] = sh.tile[(h + 16 * k) * TILE_P + ll];
         fft256(X, sh.tbuf[ll], h, sh.tab.tw);
         axis256(X, o, sh.tbuf[ll], h, sh.tab, t.a, t.pml);
-        // the line's transpose buffer is free now: park C(u) there in natural order for the coalesced epilogue
 #pragma unroll
         for (int j = 0; j < 16; j++) sh.tbuf[ll][pidx(h + 16 * j)] = o[j];
     }
-    cp_async_wait<0>();
     __syncthreads();
     float part = 0.f, lmax = 0.f;
-    constexpr int EPI_CHUNK = 8;          // source loads of a whole chunk are issued before their first use
+    constexpr int EPI_CHUNK = 8;
     const float2* srcp = a.src != nullptr ? a.src + (a.src_batch > 1 ? img : (size_t)0) + j0 : nullptr;
 #pragma unroll 1
     for (int it0 = threadIdx.x; it0 < N * LINES; it0 += THREADS * EPI_CHUNK) {
-        float2 sv[EPI_CHUNK];
+        float2 sv[EPI_CHUNK], rxv[EPI_CHUNK];
+        float kq[EPI_CHUNK];
 #pragma unroll
         for (int q = 0; q < EPI_CHUNK; q++) {
             const int it = it0 + q * THREADS;
-            sv[q] = srcp != nullptr ? __ldg(srcp + (size_t)(it >> 3) * N + (it & 7)) : make_float2(0.f, 0.f);
+            const size_t off = (size_t)(it >> 3) * N + (it & 7);
+            rxv[q] = __ldg(a.rx + img + j0 + off);
+            kq[q] = a.ksq != nullptr ? __ldg(a.ksq + img + j0 + off) : 0.f;
+            sv[q] = srcp != nullptr ? __ldg(srcp + off) : make_float2(0.f, 0.f);
         }
 #pragma unroll
         for (int q = 0; q < EPI_CHUNK; q++) {
             const int it = it0 + q * THREADS;
             const int i = it >> 3, c = it & 7;
-            float2 r = cadd(sh.rxs[it], sh.tbuf[c][pidx(i)]);
-            if (a.ksq != nullptr) {
-                const float kq = sh.ksq[it];
-                const float2 uu = sh.tile[i * TILE_P + c];
-                r.x = fmaf(kq, uu.x, r.x);
-                r.y = fmaf(kq, uu.y, r.y);
-            }
+            float2 r = cadd(rxv[q], sh.tbuf[c][pidx(i)]);
+            const float2 uu = sh.tile[i * TILE_P + c];
+            r.x = fmaf(kq[q], uu.x, r.x);
+            r.y = fmaf(kq[q], uu.y, r.y);
             r.x -= sv[q].x;
             r.y -= sv[q].y;
             a.res[img + (size_t)i * N + j0 + c] = r;
