@@ -269,34 +269,45 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
                 const int gjd = gj + es + 2;                   // input pair that completes output rows 4es .. 4es+3
                 if (!mbar_wait(pair_done + (gjd & (NDB - 1)), (uint32_t)(gjd / NDB) & 1u)) { ok = false; break; }
                 asm volatile("tcgen05.fence::after_thread_sync;");
+                // two output rows per TMEM round trip: both loads are in flight before the one wait, and the two rows'
+                // arithmetic and stores interleave (a single epilogue warp per scheduler is latency-bound otherwise)
 #pragma unroll 1
-                for (int r = 0; r < 4; r++) {
+                for (int r = 0; r < 4; r += 2) {
                     const int oyl = 4 * es + r;
-                    uint32_t v[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(((go + oyl) & 15) * UC);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                        : "r"(taddr));
+                    uint32_t v[2][32];
+                    const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16);
+                    const uint32_t taddr0 = tbase + (uint32_t)(((go + oyl) & 15) * UC), taddr1 = tbase + (uint32_t)(((go + oyl + 1) & 15) * UC);
+#pragma unroll
+                    for (int t = 0; t < 2; t++)
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                            : "=r"(v[t][0]), "=r"(v[t][1]), "=r"(v[t][2]), "=r"(v[t][3]), "=r"(v[t][4]), "=r"(v[t][5]), "=r"(v[t][6]), "=r"(v[t][7]),
+                              "=r"(v[t][8]), "=r"(v[t][9]), "=r"(v[t][10]), "=r"(v[t][11]), "=r"(v[t][12]), "=r"(v[t][13]), "=r"(v[t][14]),
+                              "=r"(v[t][15]), "=r"(v[t][16]), "=r"(v[t][17]), "=r"(v[t][18]), "=r"(v[t][19]), "=r"(v[t][20]), "=r"(v[t][21]),
+                              "=r"(v[t][22]), "=r"(v[t][23]), "=r"(v[t][24]), "=r"(v[t][25]), "=r"(v[t][26]), "=r"(v[t][27]), "=r"(v[t][28]),
+                              "=r"(v[t][29]), "=r"(v[t][30]), "=r"(v[t][31])
+                            : "r"(t == 0 ? taddr0 : taddr1));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     {
                         const uint32_t z = 0u;
-                        asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z));
+                        asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr0), "r"(z));
+                        asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr1), "r"(z));
                     }
                     if (cell < Wi) {
-                        float4* dst = reinterpret_cast<float4*>(a.out + (gs.img_out + (size_t)(2 * gs.iy0 + oyl) * Wo + 2 * cell) * 8);
 #pragma unroll
-                        for (int px = 0; px < 2; px++) {
-                            float o[8];
+                        for (int t = 0; t < 2; t++) {
+                            float4* dst = reinterpret_cast<float4*>(a.out + (gs.img_out + (size_t)(2 * gs.iy0 + oyl + t) * Wo + 2 * cell) * 8);
 #pragma unroll
-                            for (int c = 0; c < 8; c++) {
-                                o[c] = fmaf(fmaf(__uint_as_float(v[px * 16 + 8 + c]), 1.f / 2048.f, __uint_as_float(v[px * 16 + c])), out_scale, a.bias[c]);
-                                lmax = fmaxf(lmax, fabsf(o[c]));
+                            for (int px = 0; px < 2; px++) {
+                                float o[8];
+#pragma unroll
+                                for (int c = 0; c < 8; c++) {
+                                    o[c] = fmaf(fmaf(__uint_as_float(v[t][px * 16 + 8 + c]), 1.f / 2048.f, __uint_as_float(v[t][px * 16 + c])), out_scale,
+                                                a.bias[c]);
+                                    lmax = fmaxf(lmax, fabsf(o[c]));
+                                }
+                                st_nhwc8(reinterpret_cast<float*>(dst + 2 * px), o);
                             }
-                            st_nhwc8(reinterpret_cast<float*>(dst + 2 * px), o);
                         }
                     }
                 }
