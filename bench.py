@@ -305,12 +305,20 @@ def run_ours(args):
         tf32_peak = peaks["bf16_tflops"] / 2.0
         ach_tf = FLOP_PER_POINT * pts / t_unet / 1e12 if t_unet > 0 else 0.0
         ach_gb = BYTES_PER_POINT_SPECTRAL * pts / t_spec / 1e9 if t_spec > 0 else 0.0
+        # DRAM bytes per launch from the committed ncu capture of this very configuration (null for any other)
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj["config"] == {"n": n, "batch_per_gpu": b_local} and fused:
+                traffic = {int(k): v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tj["kernels"].items()}
         roof = []
         for which, name, bpp in kernel_table:
             ms_k = kern_ms[which]
             gbs = bpp * pts / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
             roof.append({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                         "traffic": None, "kernel": name, "ms_per_launch": ms_k, "algorithmic_bytes_per_point": bpp,
+                         "traffic": traffic.get(which), "algorithmic_bytes": bpp * pts, "kernel": name, "ms_per_launch": ms_k, "algorithmic_bytes_per_point": bpp,
                          "peak_source": f"{peaks['source']} (MEASURED_PEAKS.json hbm_gbs, burst copy)"})
         cpu = None
         if not args.no_cpu_baseline:
@@ -354,7 +362,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=256)
