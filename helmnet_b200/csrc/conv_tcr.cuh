@@ -158,7 +158,11 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
     constexpr int NSP = stage_ring(SRC) / 2;   // staging ring depth in row pairs
     constexpr int NPB = 8;                     // output-pair barriers: 16 accumulator units = 8 row pairs
     constexpr int NDB = 16;                    // input-pair completion barriers (deeper: halo pairs make input run ahead)
-    constexpr uint32_t kIdescBase = (1u << 4) | ((128u >> 4) << 24);   // f16 x f16 -> f32, both K-major, M=128; N field added per MMA
+    // f16 x f16 -> f32, both K-major; N field added per MMA.  M = 128 pixels of a row, or M = 64 when the image is no wider
+    // than 64 pixels (half the A-operand fetch; the accumulator rows then sit in lanes 0..15 of every 32-lane TMEM
+    // quadrant: row i -> lane 32 (i / 16) + i % 16, cute::tmem_frg_1sm "half subpartitions" layout).
+    const bool m64 = a.W <= 64;
+    const uint32_t kIdescBase = (1u << 4) | ((m64 ? (64u >> 4) : (128u >> 4)) << 24);
     extern __shared__ __align__(128) uint8_t smem_tcr[];
     uint8_t* stage = smem_tcr;                                                    // [NSP][2 rows] fp32 row segments (TMA destination)
     uint8_t* ring = stage + (size_t)NSP * 2 * stage_bytes(SRC);                   // [SRP][2 rows][G][2][PS] x 16 B operand rows
@@ -359,7 +363,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
             const uint32_t a_lo0 = (uint32_t)da, a_hi = (uint32_t)(da >> 32), b_lo = (uint32_t)db, b_hi = (uint32_t)(db >> 32);
             constexpr uint32_t kSlot16 = (uint32_t)(slot_bytes(SRC) >> 4);      // operand row pitch in 16-byte units
             constexpr uint32_t kGroup16 = 2 * PS, kB16 = BROW_BYTES / 16;
-            constexpr uint32_t kIdesc48 = kIdescBase | (6u << 17);
+            const uint32_t kIdesc48 = kIdescBase | (6u << 17);
             int gj = 0, go = 0;
 #pragma unroll 1
             for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
@@ -425,7 +429,8 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
 #pragma unroll 1
         for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
             const Strip gs = strip_of(st, a);
-            const int gx = gs.x0 + quad * 32 + lane;
+            // M = 64: quadrant q holds pixels 16 q .. 16 q + 15 in its first 16 lanes, the other lanes are idle
+            const int gx = m64 ? (lane < 16 ? gs.x0 + quad * 16 + lane : W) : gs.x0 + quad * 32 + lane;
             const int y0 = gs.y0;
             const size_t img = gs.img;
 #pragma unroll 1

@@ -76,7 +76,10 @@ __device__ __forceinline__ Strip strip_of(int st, const Args& a) {
 }
 
 __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
-    constexpr uint32_t kIdescBase = (1u << 4) | ((128u >> 4) << 24);
+    // M = 64 when the output is no wider than 64 pixels (half the A-operand fetch; accumulator row i then sits in lane
+    // 32 (i / 16) + i % 16, see conv_tcr.cuh)
+    const bool m64 = (a.W >> 1) <= 64;
+    const uint32_t kIdescBase = (1u << 4) | ((m64 ? (64u >> 4) : (128u >> 4)) << 24);
     extern __shared__ __align__(128) uint8_t smem_tcd[];
     uint8_t* stage = smem_tcd;                                          // [NSP][2] fp32 rows
     uint8_t* ring = stage + (size_t)NSP * 2 * ROW_ST_BYTES;             // [SRP][2] operand rows
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
             const uint64_t db = tc::smem_desc(tc::smem_u32(bsm), 128, 256);
             const uint32_t a_lo0 = (uint32_t)da, a_hi = (uint32_t)(da >> 32), b_lo = (uint32_t)db, b_hi = (uint32_t)(db >> 32);
             constexpr uint32_t kRow16 = ROW_OP_BYTES >> 4;
-            constexpr uint32_t kIdesc64 = kIdescBase | (8u << 17);
+            const uint32_t kIdesc64 = kIdescBase | (8u << 17);
             int gj = 0, go = 0;
 #pragma unroll 1
             for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
 #pragma unroll 1
         for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
             const Strip gs = strip_of(st, a);
-            const int ox = gs.ox0 + quad * 32 + lane;
+            const int ox = m64 ? (lane < 16 ? gs.ox0 + quad * 16 + lane : Wo) : gs.ox0 + quad * 32 + lane;
 #pragma unroll 1
             for (int oyl = 0; oyl < gs.Ro; oyl++) {
                 const int gjd = gj + oyl + 3;                  // input pair that completes output row oyl

@@ -75,7 +75,9 @@ __device__ __forceinline__ Strip strip_of(int st, const Args& a) {
 }
 
 __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
-    constexpr uint32_t kIdescBase = (1u << 4) | ((128u >> 4) << 24);
+    // M = 64 when the input is no wider than 64 cells (accumulator row i then sits in lane 32 (i / 16) + i % 16, see conv_tcr.cuh)
+    const bool m64 = a.Wi <= 64;
+    const uint32_t kIdescBase = (1u << 4) | ((m64 ? (64u >> 4) : (128u >> 4)) << 24);
     extern __shared__ __align__(128) uint8_t smem_tcu[];
     uint8_t* stage = smem_tcu;
     uint8_t* ring = stage + (size_t)NSP * 2 * ROW_ST_BYTES;
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
 #pragma unroll 1
         for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
             const Strip gs = strip_of(st, a);
-            const int cell = gs.x0 + quad * 32 + lane;
+            const int cell = m64 ? (lane < 16 ? gs.x0 + quad * 16 + lane : Wi) : gs.x0 + quad * 32 + lane;
             const int Ro = 2 * gs.Ri;
 #pragma unroll 1
             for (int es = 0; es < Ro / 4; es++) {

@@ -107,7 +107,8 @@ struct hn_ctx {
     int tc_min_res = 16;       // use the tensor-core kernels for levels with resolution >= this
     int tcr_min_res = 48;      // row-streaming tensor-core kernel for widths >= this (128-wide strips)
     int num_sms = 148;
-    int tcd_min_res = 64;      // tensor-core down-sampling for output widths >= this
+    int tcd_min_res = 64;      // tensor-core down-/up-sampling for output (input) widths >= this (M = 64 MMAs at exactly 64); 32 works
+                               // too (-1 %), but the fp32 CUDA-core kernels keep a wider margin on the README RMSE-trajectory bar
     Weights W;
     // residual norms
     double* ssq = nullptr;
