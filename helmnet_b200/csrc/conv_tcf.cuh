@@ -3,7 +3,8 @@
 //
 // Two chained row-streaming implicit GEMMs (the mapping of conv_tcr.cuh: M = 128 pixels of one image row,
 // vertical taps in N, split-fp16 operands, output-stationary TMEM accumulator rings) inside ONE persistent CTA
-// that owns FULL-WIDTH image rows (W = 128 * NH, NH = 1 or 2), so the second convolution finds the left/right
+// that owns FULL-WIDTH image rows (W = 128 * NH, NH = 1 or 2; NH = 0 stands for W = 64 with M = 64 MMAs, whose
+// accumulator row i sits in TMEM lane 32 (i / 16) + i % 16), so the second convolution finds the left/right
 // neighbours of every intermediate pixel in its own shared memory -- no halo exchange and no recomputation
 // along x; along y a strip of R output rows recomputes 2 intermediate rows.
 //
@@ -39,13 +40,15 @@ constexpr int NDB = 16;            // commit barriers per convolution
 constexpr int BROW_BYTES = 1536;   // one (group, dx) B operand: 48 x 16 fp16
 
 __host__ __device__ constexpr int groups_of(int src) { return (src == SRC_A8_B2 || src == SRC_A8_B8) ? 2 : 1; }
-__host__ __device__ constexpr int psw(int nh) { return 128 * nh + 8; }                    // operand positions per row
-__host__ __device__ constexpr int conv_warps(int nh) { return 4 * nh; }
-__host__ __device__ constexpr int epi_warps(int nh) { return 4 * nh; }
+__host__ __device__ constexpr int wpx(int nh) { return nh == 0 ? 64 : 128 * nh; }           // image width
+__host__ __device__ constexpr int halves(int nh) { return nh == 0 ? 1 : nh; }               // MMAs (M = 128 or 64) per row
+__host__ __device__ constexpr int psw(int nh) { return wpx(nh) + 8; }                       // operand positions per row
+__host__ __device__ constexpr int conv_warps(int nh) { return wpx(nh) / 32; }
+__host__ __device__ constexpr int epi_warps(int nh) { return 4 * halves(nh); }
 __host__ __device__ constexpr int threads(int nh) { return (conv_warps(nh) + 3 + 2 * epi_warps(nh)) * 32; }
-__host__ __device__ constexpr int tmem_cols(int nh) { return 2 * TR * NC * nh; }
+__host__ __device__ constexpr int tmem_cols(int nh) { return 2 * TR * NC * halves(nh); }
 __host__ __device__ constexpr size_t stage_row_bytes(int src, int nh) {
-    return (size_t)128 * nh * (src == SRC_INC ? 16 : src == SRC_A8 ? 32 : src == SRC_A8_B2 ? 40 : 64);
+    return (size_t)wpx(nh) * (src == SRC_INC ? 16 : src == SRC_A8 ? 32 : src == SRC_A8_B2 ? 40 : 64);
 }
 // ring depths in row PAIRS
 __host__ __device__ constexpr int nsp(int src, int nh) { return src == SRC_A8_B8 ? 2 : (src == SRC_INC ? 4 : 3); }
@@ -102,13 +105,14 @@ using tcr::mma_f16;
 template <int G, int NH>
 __device__ __forceinline__ void issue_row(uint32_t acc_base, uint32_t a_lo /* (half 0, group 0, dx 0) of this operand row */, uint32_t a_hi,
                                           uint32_t b_lo /* (group 0, dx 0) */, uint32_t b_hi, int k, int gk, int R) {
-    constexpr uint32_t kIdescBase = (1u << 4) | ((128u >> 4) << 24);
+    constexpr uint32_t kIdescBase = (1u << 4) | (((NH == 0 ? 64u : 128u) >> 4) << 24);
     constexpr uint32_t kGroup16 = (uint32_t)(2 * psw(NH));     // operand planes of the next channel group, in 16-byte units
+    constexpr int NHALF = halves(NH);
     constexpr uint32_t kB16 = BROW_BYTES / 16;
     if (k >= 2 && k < R && (gk & 7) >= 2) {
         const uint32_t d0 = acc_base + (uint32_t)((7 - (gk & 7)) * NC);
 #pragma unroll
-        for (int h = 0; h < NH; h++)
+        for (int h = 0; h < NHALF; h++)
 #pragma unroll
             for (int g = 0; g < G; g++)
 #pragma unroll
@@ -125,7 +129,7 @@ __device__ __forceinline__ void issue_row(uint32_t acc_base, uint32_t a_lo /* (h
             const uint32_t d0 = acc_base + (uint32_t)(u * NC);
             const uint32_t idesc = kIdescBase | ((uint32_t)(2 * len) << 17);   // N = 16 * len
 #pragma unroll
-            for (int h = 0; h < NH; h++)
+            for (int h = 0; h < NHALF; h++)
 #pragma unroll
                 for (int g = 0; g < G; g++)
 #pragma unroll
@@ -163,8 +167,9 @@ __device__ __forceinline__ int exp_of(float v) {
 
 template <int SRC, int NH, int EPI>
 __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel(Args a) {
+    static_assert(NH >= 0 && NH <= 2, "NH = 0 (64 px), 1 (128 px) or 2 (256 px)");
     constexpr int G = groups_of(SRC);
-    constexpr int W = 128 * NH;
+    constexpr int W = wpx(NH);
     constexpr int PSW = psw(NH);
     constexpr int NSP = nsp(SRC, NH), SRP1 = srp1(SRC, NH), SRP2 = srp2(SRC, NH);
     constexpr int CONV_WARPS = conv_warps(NH), EPI_WARPS = epi_warps(NH);
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
     constexpr int NCT = CONV_WARPS * 32;         // converter threads == W: one per image column
     constexpr int NET = EPI_WARPS * 32;          // threads per epilogue == W
     constexpr size_t SROW = stage_row_bytes(SRC, NH), A1ROW = a1_row_bytes(SRC, NH), A2ROW = a2_row_bytes(NH);
-    constexpr uint32_t ACC1 = 0, ACC2 = NH * TR * NC;   // TMEM column offsets of the two accumulator rings
+    constexpr uint32_t ACC1 = 0, ACC2 = halves(NH) * TR * NC;   // TMEM column offsets of the two accumulator rings
 
     extern __shared__ __align__(128) uint8_t smem_tcf[];
     uint8_t* stage = smem_tcf;                                   // [NSP][2][SROW]
@@ -447,7 +452,8 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
     } else if (warp < EPI2_WARP0) {
         // =============================== epilogue 1: accumulators -> PReLU -> operand ring A2 ========================
         const int half = (warp - EPI1_WARP0) >> 2, quad = warp & 3;
-        const int x = half * 128 + quad * 32 + lane;
+        const bool act = NH != 0 || lane < 16;      // M = 64: 16 accumulator rows per TMEM lane quadrant
+        const int x = NH == 0 ? quad * 16 + (lane & 15) : half * 128 + quad * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + ACC1 + (uint32_t)(half * TR * NC);
         int gj = 0, gmp = 0;
 #pragma unroll 1
@@ -480,8 +486,10 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
                     uint4 hi, lo;
                     tc::split8(m, mult2, hi, lo);
                     uint4* slot = reinterpret_cast<uint4*>(a2 + (size_t)(s2 * 2 + t) * A2ROW);
-                    slot[x + 1] = hi;
-                    slot[PSW + x + 1] = lo;
+                    if (act) {
+                        slot[x + 1] = hi;
+                        slot[PSW + x + 1] = lo;
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;");
                 mbar_arrive(a2_full + s2);
@@ -492,7 +500,8 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
     } else {
         // =============================== epilogue 2: accumulators -> bias / outc / update -> HBM =====================
         const int half = (warp - EPI2_WARP0) >> 2, quad = warp & 3;
-        const int x = half * 128 + quad * 32 + lane;
+        const bool act = NH != 0 || lane < 16;
+        const int x = NH == 0 ? quad * 16 + (lane & 15) : half * 128 + quad * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + ACC2 + (uint32_t)(half * TR * NC);
         float lmax = 0.f;
         int gmp = 0, gop = 0;
@@ -505,7 +514,7 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
             for (int q = 0; q < R / 2; q++) {
                 const int ya = 2 * q;
                 float2 wfa = make_float2(0.f, 0.f), wfb = wfa;
-                if (EPI == EPI_OUTC && a.dwf_out == nullptr) {   // issue the wavefield loads before waiting on the MMAs
+                if (EPI == EPI_OUTC && a.dwf_out == nullptr && act) {   // issue the wavefield loads before waiting on the MMAs
                     wfa = reinterpret_cast<const float2*>(a.wf)[img + (size_t)(y0 + ya) * W + x];
                     wfb = reinterpret_cast<const float2*>(a.wf)[img + (size_t)(y0 + ya + 1) * W + x];
                 }
@@ -518,6 +527,7 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
                 mbar_arrive(acc2_empty + (go_ & (NPB - 1)));
 #pragma unroll
                 for (int t = 0; t < 2; t++) {
+                    if (!act) break;        // M = 64: idle lanes (structured: the warp reconverges after this loop)
                     float o[8];
 #pragma unroll
                     for (int c = 0; c < 8; c++)
