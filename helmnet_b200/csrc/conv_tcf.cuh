@@ -3,7 +3,7 @@
 //
 // Two chained row-streaming implicit GEMMs (the mapping of conv_tcr.cuh: M = 128 pixels of one image row,
 // vertical taps in N, split-fp16 operands, output-stationary TMEM accumulator rings) inside ONE persistent CTA
-// that owns FULL-WIDTH image rows (W = 128 * NH, NH = 1 or 2; NH = 0 stands for W = 64 with M = 64 MMAs, whose
+// that owns FULL-WIDTH image rows (W = 128 * NH, NH = 1 or 2; NH = 0 / -1 stand for W = 64 / 32 with M = 64 MMAs, whose
 // accumulator row i sits in TMEM lane 32 (i / 16) + i % 16), so the second convolution finds the left/right
 // neighbours of every intermediate pixel in its own shared memory -- no halo exchange and no recomputation
 // along x; along y a strip of R output rows recomputes 2 intermediate rows.
@@ -40,9 +40,10 @@ constexpr int NDB = 16;            // commit barriers per convolution
 constexpr int BROW_BYTES = 1536;   // one (group, dx) B operand: 48 x 16 fp16
 
 __host__ __device__ constexpr int groups_of(int src) { return (src == SRC_A8_B2 || src == SRC_A8_B8) ? 2 : 1; }
-__host__ __device__ constexpr int wpx(int nh) { return nh == 0 ? 64 : 128 * nh; }           // image width
-__host__ __device__ constexpr int halves(int nh) { return nh == 0 ? 1 : nh; }               // MMAs (M = 128 or 64) per row
-__host__ __device__ constexpr int psw(int nh) { return wpx(nh) + 8; }                       // operand positions per row
+__host__ __device__ constexpr int wpx(int nh) { return nh < 0 ? 32 : nh == 0 ? 64 : 128 * nh; }   // image width (NH = -1: 32)
+__host__ __device__ constexpr int halves(int nh) { return nh <= 0 ? 1 : nh; }               // MMAs (M = 128 or 64) per row
+__host__ __device__ constexpr int psw(int nh) { return (nh < 0 ? 64 : wpx(nh)) + 8; }       // operand positions per row (an M = 64
+                                                                                            // MMA reads 64 of them: zeros beyond W)
 __host__ __device__ constexpr int conv_warps(int nh) { return wpx(nh) / 32; }
 __host__ __device__ constexpr int epi_warps(int nh) { return 4 * halves(nh); }
 __host__ __device__ constexpr int threads(int nh) { return (conv_warps(nh) + 3 + 2 * epi_warps(nh)) * 32; }
@@ -105,7 +106,7 @@ using tcr::mma_f16;
 template <int G, int NH>
 __device__ __forceinline__ void issue_row(uint32_t acc_base, uint32_t a_lo /* (half 0, group 0, dx 0) of this operand row */, uint32_t a_hi,
                                           uint32_t b_lo /* (group 0, dx 0) */, uint32_t b_hi, int k, int gk, int R) {
-    constexpr uint32_t kIdescBase = (1u << 4) | (((NH == 0 ? 64u : 128u) >> 4) << 24);
+    constexpr uint32_t kIdescBase = (1u << 4) | (((NH <= 0 ? 64u : 128u) >> 4) << 24);
     constexpr uint32_t kGroup16 = (uint32_t)(2 * psw(NH));     // operand planes of the next channel group, in 16-byte units
     constexpr int NHALF = halves(NH);
     constexpr uint32_t kB16 = BROW_BYTES / 16;
@@ -167,7 +168,7 @@ __device__ __forceinline__ int exp_of(float v) {
 
 template <int SRC, int NH, int EPI>
 __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel(Args a) {
-    static_assert(NH >= 0 && NH <= 2, "NH = 0 (64 px), 1 (128 px) or 2 (256 px)");
+    static_assert(NH >= -1 && NH <= 2, "NH = -1 (32 px), 0 (64 px), 1 (128 px) or 2 (256 px)");
     constexpr int G = groups_of(SRC);
     constexpr int W = wpx(NH);
     constexpr int PSW = psw(NH);
@@ -452,8 +453,8 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
     } else if (warp < EPI2_WARP0) {
         // =============================== epilogue 1: accumulators -> PReLU -> operand ring A2 ========================
         const int half = (warp - EPI1_WARP0) >> 2, quad = warp & 3;
-        const bool act = NH != 0 || lane < 16;      // M = 64: 16 accumulator rows per TMEM lane quadrant
-        const int x = NH == 0 ? quad * 16 + (lane & 15) : half * 128 + quad * 32 + lane;
+        const bool act = NH > 0 || (lane < 16 && quad * 16 < W);      // M = 64: 16 accumulator rows per TMEM lane quadrant
+        const int x = NH <= 0 ? quad * 16 + (lane & 15) : half * 128 + quad * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + ACC1 + (uint32_t)(half * TR * NC);
         int gj = 0, gmp = 0;
 #pragma unroll 1
@@ -500,8 +501,8 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
     } else {
         // =============================== epilogue 2: accumulators -> bias / outc / update -> HBM =====================
         const int half = (warp - EPI2_WARP0) >> 2, quad = warp & 3;
-        const bool act = NH != 0 || lane < 16;
-        const int x = NH == 0 ? quad * 16 + (lane & 15) : half * 128 + quad * 32 + lane;
+        const bool act = NH > 0 || (lane < 16 && quad * 16 < W);
+        const int x = NH <= 0 ? quad * 16 + (lane & 15) : half * 128 + quad * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + ACC2 + (uint32_t)(half * TR * NC);
         float lmax = 0.f;
         int gmp = 0, gop = 0;

@@ -726,7 +726,7 @@ static int launch_dconv_nh(hn_ctx* c, const tcf::Args& t0, int B, cudaStream_t s
 template <int SRC, int EPI>
 static int launch_dconv(hn_ctx* c, const ConvW (&w)[2], const float* inA, const float* inB, float* out, int r, int slot_out, int slot_in0,
                         int slot_in1, int B, cudaStream_t st, const ConvW* outc = nullptr, float* wf = nullptr, float* dwf_out = nullptr) {
-    if (c->engine < 2 || (r != 64 && r != 128 && r != 256) || w[0].tcr == (size_t)-1 || w[1].tcr == (size_t)-1 || !c->tcw) return 0;
+    if (c->engine < 2 || (r != 32 && r != 64 && r != 128 && r != 256) || w[0].tcr == (size_t)-1 || w[1].tcr == (size_t)-1 || !c->tcw) return 0;
     tcf::Args t;
     memset(&t, 0, sizeof(t));
     t.inA = inA; t.inB = inB; t.sigma = c->sigma1d;
@@ -751,6 +751,7 @@ static int launch_dconv(hn_ctx* c, const ConvW (&w)[2], const float* inA, const 
     t.H = r;
     if (r == 256) return launch_dconv_nh<SRC, 2, EPI>(c, t, B, st);
     if (r == 64) return launch_dconv_nh<SRC, 0, EPI>(c, t, B, st);
+    if (r == 32) return launch_dconv_nh<SRC, -1, EPI>(c, t, B, st);
     return launch_dconv_nh<SRC, 1, EPI>(c, t, B, st);
 }
 #define HN_TRY_DCONV(var, expr) \
