@@ -68,6 +68,8 @@ struct Args {
     const float* sigma;
     const __half* bmat1;        // first conv: [groups][3 dx] x 1536 B (pack_tcr)
     const __half* bmat2;        // second conv: [3 dx] x 1536 B
+    const __half* bfold1;       // SRC_A8_B2: the 2-channel group of the first conv with its 3 dx taps folded into K (1536 B)
+    const __half* bfold2;       // EPI_STORE2: the 2 -> 2 second conv, dx folded into K (1536 B)
     // small per-layer constants travel as kernel parameters: the epilogues read them straight from the constant bank
     // (operand form c[0x0][..] of FFMA) instead of re-loading them from shared memory after every tcgen05.wait
     float bias1[8];             // zero padded
@@ -103,7 +105,11 @@ using tcr::mma_f16;
 // MMAs of ONE operand row: local row k of a strip whose conv has R live output rows; gk = global index of the output
 // row with the same index (dy = 0).  The accumulator of output row y lives in unit 7 - (y & 7), so rows k, k-1, k-2
 // are ascending adjacent units (split at the ring wrap).  acc_base: TMEM column of (half 0, unit 0) of this conv.
-template <int G, int NH>
+// FOLD: the LAST channel group carries only 2 channels (hidden state / 2-channel intermediate); its three horizontal
+// taps are folded into K -- operand entry e holds [pixel e-2 | pixel e-1] (hi2 lo2 each) in plane 0 and [pixel e | 0]
+// in plane 1, so ONE MMA at the centre position (start entry m + 1) covers dx = 0, 1, 2 against the B image
+// k = dx * 4 + part * 2 + c (pack_tcf_fold): 1 MMA instead of 3 for that group.
+template <int G, int NH, bool FOLD>
 __device__ __forceinline__ void issue_row(uint32_t acc_base, uint32_t a_lo /* (half 0, group 0, dx 0) of this operand row */, uint32_t a_hi,
                                           uint32_t b_lo /* (group 0, dx 0) */, uint32_t b_hi, int k, int gk, int R) {
     constexpr uint32_t kIdescBase = (1u << 4) | (((NH <= 0 ? 64u : 128u) >> 4) << 24);
@@ -115,11 +121,17 @@ __device__ __forceinline__ void issue_row(uint32_t acc_base, uint32_t a_lo /* (h
 #pragma unroll
         for (int h = 0; h < NHALF; h++)
 #pragma unroll
-            for (int g = 0; g < G; g++)
+            for (int g = 0; g < G; g++) {
+                if (FOLD && g == G - 1) {
+                    mma_f16(d0 + (uint32_t)(h * TR * NC), a_lo + (uint32_t)(h * 128 + 1) + g * kGroup16, a_hi,
+                            b_lo + (uint32_t)(g * 3) * kB16, b_hi, kIdescBase | (6u << 17));
+                } else {
 #pragma unroll
-                for (int dx = 0; dx < 3; dx++)
-                    mma_f16(d0 + (uint32_t)(h * TR * NC), a_lo + (uint32_t)(h * 128 + dx) + g * kGroup16, a_hi,
-                            b_lo + (uint32_t)(g * 3 + dx) * kB16, b_hi, kIdescBase | (6u << 17));
+                    for (int dx = 0; dx < 3; dx++)
+                        mma_f16(d0 + (uint32_t)(h * TR * NC), a_lo + (uint32_t)(h * 128 + dx) + g * kGroup16, a_hi,
+                                b_lo + (uint32_t)(g * 3 + dx) * kB16, b_hi, kIdescBase | (6u << 17));
+                }
+            }
     } else {
         const int dlo = max(0, k - (R - 1)), dhi = min(2, k);
         int dy = dlo;
@@ -132,14 +144,37 @@ __device__ __forceinline__ void issue_row(uint32_t acc_base, uint32_t a_lo /* (h
 #pragma unroll
             for (int h = 0; h < NHALF; h++)
 #pragma unroll
-                for (int g = 0; g < G; g++)
+                for (int g = 0; g < G; g++) {
+                    if (FOLD && g == G - 1) {
+                        mma_f16(d0 + (uint32_t)(h * TR * NC), a_lo + (uint32_t)(h * 128 + 1) + g * kGroup16, a_hi,
+                                b_lo + (uint32_t)(g * 3) * kB16 + (uint32_t)(dy * 32), b_hi, idesc);
+                    } else {
 #pragma unroll
-                    for (int dx = 0; dx < 3; dx++)
-                        mma_f16(d0 + (uint32_t)(h * TR * NC), a_lo + (uint32_t)(h * 128 + dx) + g * kGroup16, a_hi,
-                                b_lo + (uint32_t)(g * 3 + dx) * kB16 + (uint32_t)(dy * 32), b_hi, idesc);
+                        for (int dx = 0; dx < 3; dx++)
+                            mma_f16(d0 + (uint32_t)(h * TR * NC), a_lo + (uint32_t)(h * 128 + dx) + g * kGroup16, a_hi,
+                                    b_lo + (uint32_t)(g * 3 + dx) * kB16 + (uint32_t)(dy * 32), b_hi, idesc);
+                    }
+                }
             dy += len;
         }
     }
+}
+
+// Two channels -> [hi c0, hi c1, lo c0, lo c1] (8 bytes): the split of tc::split8 for one channel pair.
+__device__ __forceinline__ uint2 split2(float v0, float v1, float mult) {
+    const float a = v0 * mult, b = v1 * mult;
+    const __half2 hh = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn((a - back.x) * 2048.f, (b - back.y) * 2048.f);
+    return make_uint2(*reinterpret_cast<const uint32_t*>(&hh), *reinterpret_cast<const uint32_t*>(&ll));
+}
+// Store pixel x of a folded 2-channel group: `planes` = plane 0 of the group (plane 1 is PSW entries further).
+template <int PSW>
+__device__ __forceinline__ void store_fold(uint4* planes, int x, uint2 v) {
+    uint2* f = reinterpret_cast<uint2*>(planes);
+    f[2 * (x + 2)] = v;             // entry x + 2, dx = 0 field: GEMM row x + 1 sees its left neighbour
+    f[2 * (x + 1) + 1] = v;         // entry x + 1, dx = 1 field: GEMM row x, centre tap
+    f[2 * (PSW + x)] = v;           // plane 1, entry x, dx = 2 field: GEMM row x - 1 sees its right neighbour
 }
 
 // Read the accumulators of output rows (gr, gr + 1) (gr even, global row index) of this thread's TMEM lane, then hand
@@ -170,6 +205,8 @@ template <int SRC, int NH, int EPI>
 __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel(Args a) {
     static_assert(NH >= -1 && NH <= 2, "NH = -1 (32 px), 0 (64 px), 1 (128 px) or 2 (256 px)");
     constexpr int G = groups_of(SRC);
+    constexpr bool FOLD1 = SRC == SRC_A8_B2;     // hidden-state group of the first conv: dx folded into K
+    constexpr bool FOLD2 = EPI == EPI_STORE2;    // 2 -> 2 second conv: dx folded into K
     constexpr int W = wpx(NH);
     constexpr int PSW = psw(NH);
     constexpr int NSP = nsp(SRC, NH), SRP1 = srp1(SRC, NH), SRP2 = srp2(SRC, NH);
@@ -225,8 +262,18 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
         const uint4* bg2 = reinterpret_cast<const uint4*>(a.bmat2);
         uint4* bs1 = reinterpret_cast<uint4*>(b1);
         uint4* bs2 = reinterpret_cast<uint4*>(b2);
-        for (int i = tid; i < G * 3 * BROW_BYTES / 16; i += THREADS) bs1[i] = __ldg(bg1 + i);
-        for (int i = tid; i < 3 * BROW_BYTES / 16; i += THREADS) bs2[i] = __ldg(bg2 + i);
+        constexpr int NB1 = FOLD1 ? 3 : G * 3;       // images taken from bmat1 (FOLD1: group 0 only, then the folded image)
+        for (int i = tid; i < NB1 * BROW_BYTES / 16; i += THREADS) bs1[i] = __ldg(bg1 + i);
+        if constexpr (FOLD1) {
+            const uint4* bf = reinterpret_cast<const uint4*>(a.bfold1);
+            for (int i = tid; i < BROW_BYTES / 16; i += THREADS) bs1[3 * BROW_BYTES / 16 + i] = __ldg(bf + i);
+        }
+        if constexpr (FOLD2) {
+            const uint4* bf = reinterpret_cast<const uint4*>(a.bfold2);
+            for (int i = tid; i < BROW_BYTES / 16; i += THREADS) bs2[i] = __ldg(bf + i);
+        } else {
+            for (int i = tid; i < 3 * BROW_BYTES / 16; i += THREADS) bs2[i] = __ldg(bg2 + i);
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;");
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -367,7 +414,9 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
                     tc::split8(g0, mult1, hi, lo);
                     slot[x + 1] = hi;
                     slot[PSW + x + 1] = lo;
-                    if constexpr (G == 2) {
+                    if constexpr (FOLD1) {
+                        store_fold<PSW>(slot + 2 * PSW, x, split2(g1[0], g1[1], mult1));
+                    } else if constexpr (G == 2) {
                         tc::split8(g1, mult1, hi, lo);
                         slot[2 * PSW + x + 1] = hi;
                         slot[3 * PSW + x + 1] = lo;
@@ -405,7 +454,7 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
 #pragma unroll
                         for (int t = 0; t < 2; t++) {
                             const int k = 2 * j + t;
-                            issue_row<G, NH>(tb, a_lo + (uint32_t)(s * 2 + t) * kRow16, a_hi, b_lo, b_hi, k, 2 * gmp + k, RM);
+                            issue_row<G, NH, FOLD1>(tb, a_lo + (uint32_t)(s * 2 + t) * kRow16, a_hi, b_lo, b_hi, k, 2 * gmp + k, RM);
                         }
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc::smem_u32(c1_done + (g_ & (NDB - 1)))));
                     }
@@ -440,7 +489,7 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
 #pragma unroll
                         for (int t = 0; t < 2; t++) {
                             const int k = 2 * p + t;
-                            issue_row<1, NH>(tb, a_lo + (uint32_t)(s * 2 + t) * kRow16, a_hi, b_lo, b_hi, k, 2 * gop + k, R);
+                            issue_row<1, NH, FOLD2>(tb, a_lo + (uint32_t)(s * 2 + t) * kRow16, a_hi, b_lo, b_hi, k, 2 * gop + k, R);
                         }
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc::smem_u32(c2_done + (g_ & (NDB - 1)))));
                     }
@@ -484,12 +533,16 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
                         o = o >= 0.f ? o : slope * o;
                         m[c] = inside ? o : 0.f;
                     }
-                    uint4 hi, lo;
-                    tc::split8(m, mult2, hi, lo);
                     uint4* slot = reinterpret_cast<uint4*>(a2 + (size_t)(s2 * 2 + t) * A2ROW);
-                    if (act) {
-                        slot[x + 1] = hi;
-                        slot[PSW + x + 1] = lo;
+                    if constexpr (FOLD2) {
+                        if (act) store_fold<PSW>(slot, x, split2(m[0], m[1], mult2));
+                    } else {
+                        uint4 hi, lo;
+                        tc::split8(m, mult2, hi, lo);
+                        if (act) {
+                            slot[x + 1] = hi;
+                            slot[PSW + x + 1] = lo;
+                        }
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;");

@@ -60,6 +60,7 @@ struct ConvW {      // offsets (in floats) into the packed device blob
     size_t raw = 0;           // unpacked checkpoint layout [co][ci][3][3] (lean 2->2 state kernel)
     size_t tc = (size_t)-1;   // offset (in halfs) of the tcgen05 B-operand image, C_out = 8 layers only
     size_t tcr = (size_t)-1;  // same for the row-streaming kernel (N = 48 images)
+    size_t tcf = (size_t)-1;  // fused DoubleConv kernel: the 2-channel group with its 3 dx taps folded into K (one N = 48 image)
     float tc_inv = 1.f;       // 2^-kw, inverse of the layer's weight block scale
     float l1 = 0.f, bmax = 0.f;   // max_co sum |W[co]| and max |b|: bound of the layer's output (fused DoubleConv mid scale)
 };
@@ -363,6 +364,33 @@ static void pack_tcr(Packer& pk, const float* w, int cin, ConvW& out, int cout =
                     pk.halfs[out.tcr + (size_t)(g * 3 + dx) * 768 + byte / 2] = bits;
                 }
 }
+// Fused DoubleConv kernel (conv_tcf.cuh), 2-channel group (input channels ci0, ci0 + 1) with the three horizontal taps
+// folded into K:  ONE 48 x 16 image, column n = dy*16 + h*8 + co as in pack_tcr, row k = dx*4 + part*2 + c
+// (part 0: the activation's hi half, part 1: its lo half; k = 12..15 zero).  Same block scale as pack_tcr of the layer.
+static void pack_tcf_fold(Packer& pk, const float* w, int cin, int ci0, ConvW& out, int cout) {
+    float mx = 0.f;
+    for (int i = 0; i < cout * cin * 9; i++) mx = fmaxf(mx, fabsf(w[i]));
+    int ex = 0;
+    if (mx > 0.f) frexpf(mx, &ex);
+    const int kw = 10 - ex;
+    const float scale = ldexpf(1.f, kw);
+    out.tcf = pk.halfs.size();
+    pk.halfs.resize(out.tcf + 768, 0);
+    for (int n = 0; n < 48; n++)
+        for (int k = 0; k < 12; k++) {
+            const int dy = n / 16, h = (n / 8) & 1, co = n & 7, dx = k / 4, part = (k / 2) & 1, ci = ci0 + (k & 1);
+            const float wv = co < cout ? w[(co * cin + ci) * 9 + dy * 3 + dx] * scale : 0.f;
+            const __half hi = __float2half_rn(wv);
+            const __half lo = __float2half_rn((wv - __half2float(hi)) * 2048.f);
+            __half val = __float2half_rn(0.f);
+            if (h == 0) { if (part == 0) val = hi; }
+            else val = (part == 0) ? lo : hi;
+            const int byte = (n / 8) * 256 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2;
+            uint16_t bits;
+            memcpy(&bits, &val, 2);
+            pk.halfs[out.tcf + byte / 2] = bits;
+        }
+}
 // Down-sampling conv on tensor cores (conv_tcr_down.cuh): W[co][ci][8][8] -> per (t = ky parity, kx) a 64 x 16 fp16
 // B operand, column n = m*16 + h*8 + co with ky = 2m + t.
 static void pack_tcd(Packer& pk, const float* w, ConvW& out) {
@@ -470,6 +498,8 @@ static void pack_double_conv(Packer& pk, Cursor& cur, ConvW out[2], int cin, int
     if (cmid == 2 && cin == 10) pack_tcr(pk, w0, cin, out[0], 2);   // conv_state.0: C_out = 2 padded to 8 accumulator columns
     if (cout == 8 && cmid == 8) { pack_tc(pk, w1, cmid, out[1]); pack_tcr(pk, w1, cmid, out[1]); }
     if (cout == 2 && cmid == 2) pack_tcr(pk, w1, cmid, out[1], 2);  // conv_state.2 for the fused DoubleConv kernel
+    if (cin == 10) pack_tcf_fold(pk, w0, cin, 8, out[0], cmid);     // hidden-state channels of cat[x, state]
+    if (cout == 2 && cmid == 2) pack_tcf_fold(pk, w1, cmid, 0, out[1], 2);
 #endif
 }
 
@@ -732,6 +762,14 @@ static int launch_dconv(hn_ctx* c, const ConvW (&w)[2], const float* inA, const 
     t.inA = inA; t.inB = inB; t.sigma = c->sigma1d;
     t.bmat1 = reinterpret_cast<const __half*>(c->tcw + w[0].tcr);
     t.bmat2 = reinterpret_cast<const __half*>(c->tcw + w[1].tcr);
+    if (SRC == SRC_A8_B2) {
+        if (w[0].tcf == (size_t)-1) return 0;
+        t.bfold1 = reinterpret_cast<const __half*>(c->tcw + w[0].tcf);
+    }
+    if (EPI == EPI_STORE2) {
+        if (w[1].tcf == (size_t)-1) return 0;
+        t.bfold2 = reinterpret_cast<const __half*>(c->tcw + w[1].tcf);
+    }
     const float* hw = c->whost.data();
     for (int i = 0; i < 8; i++) { t.bias1[i] = hw[w[0].b8 + i]; t.bias2[i] = hw[w[1].b8 + i]; }
     t.slope = hw[w[0].slope];
