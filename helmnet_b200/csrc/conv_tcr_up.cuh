@@ -31,7 +31,7 @@ using tcr::mbar_arrive;
 using tcr::mbar_arrive_expect_tx;
 using tcr::tma_load_1d;
 
-constexpr int ROWS_I = 16;                 // input rows per strip (32 output rows)
+constexpr int ROWS_I = 16;                 // default input rows per strip (Args::rows_i; the host picks it per launch)
 constexpr int UC = 32;                     // accumulator columns per output row: 2 px x (g1 8 | g2 8)
 constexpr int TMEM_COLS = 512;
 constexpr int SRP = 4;                     // operand ring depth (input row pairs)
@@ -55,6 +55,7 @@ struct Args {
     float w_inv_scale;
     int Hi, Wi;
     int nsx, nsy, total_strips;
+    int rows_i;                 // input rows per strip (even)
 };
 
 struct Strip {
@@ -66,8 +67,8 @@ __device__ __forceinline__ Strip strip_of(int st, const Args& a) {
     const int sx = st % a.nsx, r = st / a.nsx;
     const int sy = r % a.nsy, b = r / a.nsy;
     g.x0 = sx * CW;
-    g.iy0 = sy * ROWS_I;
-    g.Ri = min(ROWS_I, a.Hi - g.iy0);     // even
+    g.iy0 = sy * a.rows_i;
+    g.Ri = min(a.rows_i, a.Hi - g.iy0);   // even
     g.NP = (g.Ri + 4) / 2;                // input rows k = 0 .. Ri + 3, image row iy0 - 2 + k
     g.img_in = (size_t)b * a.Hi * a.Wi;
     g.img_out = g.img_in * 4;

@@ -704,7 +704,22 @@ static int launch_up(hn_ctx* c, int d, int B, cudaStream_t st) {
         t.Hi = r / 2;
         t.Wi = r / 2;
         t.nsx = (r / 2 + tcr::CW - 1) / tcr::CW;
-        t.nsy = (r / 2 + tcu::ROWS_I - 1) / tcu::ROWS_I;
+        {
+            // input rows per strip: whole rounds of equal strips over one CTA per SM; a strip of R rows streams R + 4 rows
+            // (+ ~2 row steps of pipeline fill)
+            int best = tcu::ROWS_I;
+            long long best_cost = -1;
+            const int env_rows = getenv("HELMNET_UP_ROWS") ? atoi(getenv("HELMNET_UP_ROWS")) : 0;
+            for (int rows = 8; rows <= 128 && rows <= t.Hi; rows += 2) {
+                if (t.Hi % rows != 0) continue;
+                const long long total = (long long)t.nsx * (t.Hi / rows) * B;
+                const long long g = total < c->num_sms ? total : c->num_sms;
+                const long long cost = ((total + g - 1) / g) * (rows + 6);
+                if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = rows; }
+            }
+            t.rows_i = (env_rows >= 2 && env_rows % 2 == 0) ? env_rows : best;
+        }
+        t.nsy = (t.Hi + t.rows_i - 1) / t.rows_i;
         t.total_strips = t.nsx * t.nsy * B;
         const int tgrid = t.total_strips < c->num_sms ? t.total_strips : c->num_sms;   // one CTA per SM (owns all 512 TMEM columns)
         tcu::up_tcr_kernel<<<dim3(tgrid), dim3(tcr::THREADS), tcu::SMEM_BYTES, st>>>(t);
