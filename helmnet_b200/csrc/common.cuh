@@ -22,6 +22,36 @@
 #define HN_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
+// Programmatic dependent launch (PDL): every kernel of a solver iteration is launched with the programmatic stream
+// serialization attribute (when hn_ctx::pdl is set), so its CTAs may become resident while the previous kernel of the
+// stream / graph is still draining.  Each such kernel calls pdl_wait() before its first access to anything an earlier
+// kernel wrote (or still reads) -- only its own prologue (mbarrier init, TMEM allocation, constant weight / table loads
+// into shared memory) runs ahead -- and pdl_trigger() right after, which lets the NEXT kernel's CTAs take the SM slots
+// this grid frees.  Without the launch attribute both are no-ops.
+#ifdef HN_EMU
+#define HN_LAUNCH_PDL(pdl, kernel, grid, block, smem, stream, ...) HN_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__)
+#else
+namespace hn {
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(static_cast<Args&&>(args))...);
+}
+}  // namespace hn
+// (used inside functions that return an hn status: a launch error is reported through HN_CUDA)
+#define HN_LAUNCH_PDL(pdl, kernel, grid, block, smem, stream, ...) \
+    HN_CUDA(hn::launch_pdl((pdl), kernel, dim3(grid), dim3(block), (size_t)(smem), (stream), __VA_ARGS__))
+#endif
+
 // dynamic shared memory of the running CTA
 #ifdef HN_EMU
 #define HN_DYN_SMEM(type, name) \
@@ -50,6 +80,27 @@ __device__ __forceinline__ void ffma2(float2& d, float a, float2 b) {
         "mov.b64 {%0, %1}, rc; }"
         : "+f"(d.x), "+f"(d.y)
         : "f"(a), "f"(b.x), "f"(b.y));
+#endif
+}
+
+// see HN_LAUNCH_PDL above
+__device__ __forceinline__ void pdl_wait() {
+#ifndef HN_EMU
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_trigger() {
+#ifndef HN_EMU
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+// a 32-bit word another kernel of the same stream may have written while this grid was already resident (PDL): read it
+// through L2, never from a (non-coherent) L1 / read-only cache line
+__device__ __forceinline__ unsigned ld_fresh(const unsigned* p) {
+#ifdef HN_EMU
+    return *p;
+#else
+    return __ldcg(p);
 #endif
 }
 

@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(C3_THREADS) conv3x3_kernel(Conv3Args a) {
         float4* ws4 = reinterpret_cast<float4*>(wsm);
         for (int i = tid; i < NW4; i += C3_THREADS) ws4[i] = __ldg(wg + i);
     }
+    pdl_wait();      // constant weights above; activations written by earlier kernels below (common.cuh: HN_LAUNCH_PDL)
+    pdl_trigger();
     // ---- input tile (zero padded) -> smem planes --------------------------------------------------
     const size_t img = (size_t)b * H * W;
     if (SRC == SRC_A8 || SRC == SRC_A8_B2 || SRC == SRC_A8_B8) {
@@ -286,6 +288,8 @@ __global__ void __launch_bounds__(DN_THREADS) down_kernel(DownArgs a) {
         float4* ws4 = reinterpret_cast<float4*>(wsm);
         for (int i = tid; i < 2 * 64 * 4 * 8 / 4; i += DN_THREADS) ws4[i] = __ldg(wg + i);
     }
+    pdl_wait();      // constant weights above; activations written by earlier kernels below (common.cuh: HN_LAUNCH_PDL)
+    pdl_trigger();
     const size_t img = (size_t)b * H * W;
     for (int i = tid; i < DN_IW * DN_IH * 2; i += DN_THREADS) {
         const int px = i >> 1, half = i & 1;
@@ -384,6 +388,8 @@ __global__ void __launch_bounds__(UP_THREADS) up_kernel(UpArgs a) {
         float4* ws4 = reinterpret_cast<float4*>(wsm);
         for (int i = tid; i < 4 * 2 * 16 * 4 * 8 / 4; i += UP_THREADS) ws4[i] = __ldg(wg + i);
     }
+    pdl_wait();      // constant weights above; activations written by earlier kernels below (common.cuh: HN_LAUNCH_PDL)
+    pdl_trigger();
     const size_t img = (size_t)b * Hi * Wi;
     for (int i = tid; i < UP_PLANE * 2; i += UP_THREADS) {
         const int px = i >> 1, half = i & 1;
@@ -477,6 +483,8 @@ __global__ void __launch_bounds__(S2_THREADS) state2_kernel(State2Args a) {
     const size_t img = (size_t)b * H * W;
     if (tid < 36) wsm[tid] = __ldg(a.w + tid);
     if (tid >= 64 && tid < 66) wsm[36 + tid - 64] = __ldg(a.bias + tid - 64);
+    pdl_wait();      // constant weights above; activations written by earlier kernels below (common.cuh: HN_LAUNCH_PDL)
+    pdl_trigger();
     for (int i = tid; i < (S2_TY + 2) * S2_PITCH; i += S2_THREADS) {
         const int y = i / S2_PITCH, x = i - y * S2_PITCH;
         const int gy = ty0 - 1 + y, gx = tx0 - 1 + x;

@@ -129,6 +129,8 @@ __global__ void __launch_bounds__(THREADS, (groups_of(SRC) == 1) ? 4 : 2) conv3x
         for (int i = tid; i < G * 9 * BBLK_BYTES / 16; i += THREADS) bs[i] = __ldg(bg + i);
     }
 
+    pdl_wait();      // TMEM / barriers / weight images above; activations of earlier kernels below (common.cuh: HN_LAUNCH_PDL)
+    pdl_trigger();
     // ---- stage the input tile in registers, find the tile's max |x| ---------------------------------------
     // g0 / g1: the 8-channel K groups of the (virtual) concatenated input, zero padded
     float g0[PER_THREAD][8];
@@ -183,8 +185,8 @@ __global__ void __launch_bounds__(THREADS, (groups_of(SRC) == 1) ? 4 : 2) conv3x
 #pragma unroll
         for (int w = 1; w < THREADS / 32; w++) amax = fmaxf(amax, red[w]);
     } else {
-        unsigned mb = __ldg(a.amax_in0);
-        if (G == 2) mb = max(mb, __ldg(a.amax_in1));
+        unsigned mb = ld_fresh(a.amax_in0);
+        if (G == 2) mb = max(mb, ld_fresh(a.amax_in1));
         amax = __uint_as_float(mb);
     }
     // block scale: x' = x * 2^sa with max|x'| in [2^13, 2^14); exact powers of two built from exponent bits

@@ -294,13 +294,17 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
 
+    // everything above touched only this CTA's shared memory / TMEM and the constant weight images: from here on the kernel
+    // reads what earlier kernels of the iteration wrote (common.cuh: HN_LAUNCH_PDL)
+    pdl_wait();
+    pdl_trigger();
     // ---- block scales ---------------------------------------------------------------------------------------
     float amax_in;
     if constexpr (SRC == SRC_INC) {
-        amax_in = fmaxf(fmaxf(__uint_as_float(__ldg(a.amax_in0)), 1e3f * __uint_as_float(__ldg(a.amax_in1))), a.sigma_max);
+        amax_in = fmaxf(fmaxf(__uint_as_float(ld_fresh(a.amax_in0)), 1e3f * __uint_as_float(ld_fresh(a.amax_in1))), a.sigma_max);
     } else {
-        unsigned mb = __ldg(a.amax_in0);
-        if (G == 2) mb = max(mb, __ldg(a.amax_in1));
+        unsigned mb = ld_fresh(a.amax_in0);
+        if (G == 2) mb = max(mb, ld_fresh(a.amax_in1));
         amax_in = __uint_as_float(mb);
     }
     const int e_in = exp_of(amax_in);

@@ -222,13 +222,17 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
 
+    // everything above touched only this CTA's shared memory / TMEM and the constant weight images: from here on the kernel
+    // reads what earlier kernels of the iteration wrote (common.cuh: HN_LAUNCH_PDL)
+    pdl_wait();
+    pdl_trigger();
     // block scale of the activations (see conv_tc.cuh): x' = x * 2^sa, max|x'| in [2^13, 2^14)
     float amax;
     if constexpr (SRC == SRC_INC) {
-        amax = fmaxf(fmaxf(__uint_as_float(__ldg(a.amax_in0)), 1e3f * __uint_as_float(__ldg(a.amax_in1))), a.sigma_max);
+        amax = fmaxf(fmaxf(__uint_as_float(ld_fresh(a.amax_in0)), 1e3f * __uint_as_float(ld_fresh(a.amax_in1))), a.sigma_max);
     } else {
-        unsigned mb = __ldg(a.amax_in0);
-        if (G == 2) mb = max(mb, __ldg(a.amax_in1));
+        unsigned mb = ld_fresh(a.amax_in0);
+        if (G == 2) mb = max(mb, ld_fresh(a.amax_in1));
         amax = __uint_as_float(mb);
     }
     int e = (int)((__float_as_uint(amax) >> 23) & 0xffu);

@@ -132,7 +132,11 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    const float amax = __uint_as_float(__ldg(a.amax_in));
+    // everything above touched only this CTA's shared memory / TMEM and the constant weight images: from here on the kernel
+    // reads what earlier kernels of the iteration wrote (common.cuh: HN_LAUNCH_PDL)
+    pdl_wait();
+    pdl_trigger();
+    const float amax = __uint_as_float(ld_fresh(a.amax_in));
     int e = (int)((__float_as_uint(amax) >> 23) & 0xffu);
     if (e < 40 || e > 250) e = 127;
     const float mult = __uint_as_float((uint32_t)(267 - e) << 23);

@@ -108,6 +108,7 @@ struct hn_ctx {
     int tc_min_res = 16;       // use the tensor-core kernels for levels with resolution >= this
     int tcr_min_res = 48;      // row-streaming tensor-core kernel for widths >= this (128-wide strips)
     int num_sms = 148;
+    bool pdl = false;          // programmatic dependent launch for the kernels of an iteration (common.cuh: HN_LAUNCH_PDL)
     int tcd_min_res = 64;      // tensor-core down-/up-sampling for output (input) widths >= this (M = 64 MMAs at exactly 64); 32 works
                                // too (-1 %), but the fp32 CUDA-core kernels keep a wider margin on the README RMSE-trajectory bar
     Weights W;
@@ -536,7 +537,7 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
             t.nsy = (a.H + tcr::ROWS - 1) / tcr::ROWS;
             t.total_strips = t.nsx * t.nsy * B;
             const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;
-            tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI_STORE2><<<dim3(tgrid), dim3(tcr::THREADS), tcr::smem_bytes(SRC), st>>>(t);
+            HN_LAUNCH_PDL(c->pdl, (tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI_STORE2>), dim3(tgrid), dim3(tcr::THREADS), tcr::smem_bytes(SRC), st, t);
             c->launches++;
             return HN_OK;
         }
@@ -560,7 +561,7 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
             t.nsy = (a.H + tcr::ROWS - 1) / tcr::ROWS;
             t.total_strips = t.nsx * t.nsy * B;
             const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;   // persistent: 2 CTAs per SM
-            tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI><<<dim3(tgrid), dim3(tcr::THREADS), tcr::smem_bytes(SRC), st>>>(t);
+            HN_LAUNCH_PDL(c->pdl, (tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI>), dim3(tgrid), dim3(tcr::THREADS), tcr::smem_bytes(SRC), st, t);
             c->launches++;
             return HN_OK;
         }
@@ -578,14 +579,14 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
             t.amax_in0 = a.amax_in0; t.amax_in1 = a.amax_in1; t.amax_out = a.amax_out;
             t.error_flag = c->err_flag; t.w_inv_scale = a.tc_inv; t.H = a.H; t.W = a.W;
             dim3 tgrid((a.W + tc::TX - 1) / tc::TX, (a.H + tc::TY - 1) / tc::TY, B);
-            tc::conv3x3_tc_kernel<SRC, PRELU, EPI><<<tgrid, dim3(tc::THREADS), tc::smem_bytes(SRC), st>>>(t);
+            HN_LAUNCH_PDL(c->pdl, (tc::conv3x3_tc_kernel<SRC, PRELU, EPI>), tgrid, dim3(tc::THREADS), tc::smem_bytes(SRC), st, t);
             c->launches++;
             return HN_OK;
         }
     }
 #endif
     dim3 grid((a.W + C3_TX - 1) / C3_TX, (a.H + C3_TY - 1) / C3_TY, B);
-    HN_LAUNCH((conv3x3_kernel<SRC, COUT, PRELU, EPI>), grid, dim3(C3_THREADS), smem, st, a);
+    HN_LAUNCH_PDL(c->pdl, (conv3x3_kernel<SRC, COUT, PRELU, EPI>), grid, dim3(C3_THREADS), smem, st, a);
     c->launches++;
     return HN_OK;
 }
@@ -663,13 +664,13 @@ static int launch_down(hn_ctx* c, int d, int B, cudaStream_t st) {
         t.nsy = (r / 2 + tcd::ROWS_O - 1) / tcd::ROWS_O;
         t.total_strips = t.nsx * t.nsy * B;
         const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;
-        tcd::down_tcr_kernel<<<dim3(tgrid), dim3(tcr::THREADS), tcd::SMEM_BYTES, st>>>(t);
+        HN_LAUNCH_PDL(c->pdl, (tcd::down_tcr_kernel), dim3(tgrid), dim3(tcr::THREADS), tcd::SMEM_BYTES, st, t);
         c->launches++;
         return HN_OK;
     }
 #endif
     dim3 g((r / 2 + DN_TX - 1) / DN_TX, (r / 2 + DN_TY - 1) / DN_TY, B);
-    HN_LAUNCH(down_kernel, g, dim3(DN_THREADS), DN_SMEM, st, dn);
+    HN_LAUNCH_PDL(c->pdl, down_kernel, g, dim3(DN_THREADS), DN_SMEM, st, dn);
     c->launches++;
     return HN_OK;
 }
@@ -722,13 +723,13 @@ static int launch_up(hn_ctx* c, int d, int B, cudaStream_t st) {
         t.nsy = (t.Hi + t.rows_i - 1) / t.rows_i;
         t.total_strips = t.nsx * t.nsy * B;
         const int tgrid = t.total_strips < c->num_sms ? t.total_strips : c->num_sms;   // one CTA per SM (owns all 512 TMEM columns)
-        tcu::up_tcr_kernel<<<dim3(tgrid), dim3(tcr::THREADS), tcu::SMEM_BYTES, st>>>(t);
+        HN_LAUNCH_PDL(c->pdl, (tcu::up_tcr_kernel), dim3(tgrid), dim3(tcr::THREADS), tcu::SMEM_BYTES, st, t);
         c->launches++;
     } else
 #endif
     {
         dim3 g((r / 2 + UP_TL - 1) / UP_TL, (r / 2 + UP_TL - 1) / UP_TL, B);
-        HN_LAUNCH(up_kernel, g, dim3(UP_THREADS), UP_SMEM, st, up);
+        HN_LAUNCH_PDL(c->pdl, up_kernel, g, dim3(UP_THREADS), UP_SMEM, st, up);
         c->launches++;
     }
     return HN_OK;
@@ -764,7 +765,7 @@ static int launch_dconv_nh(hn_ctx* c, const tcf::Args& t0, int B, cudaStream_t s
     t.spi = (t.H + t.rows - 1) / t.rows;
     t.total_strips = t.spi * B;
     const int grid = t.total_strips < cap ? t.total_strips : cap;
-    tcf::dconv_tcf_kernel<SRC, NH, EPI><<<dim3(grid), dim3(tcf::threads(NH)), tcf::smem_bytes(SRC, NH), st>>>(t);
+    HN_LAUNCH_PDL(c->pdl, (tcf::dconv_tcf_kernel<SRC, NH, EPI>), dim3(grid), dim3(tcf::threads(NH)), tcf::smem_bytes(SRC, NH), st, t);
     c->launches++;
     return 1;
 }
@@ -827,7 +828,7 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
         mask &= ~(1ull << S_IN6);
         mask &= ~(1ull << (S_WF + cur));
         mask &= ~(1ull << (S_RES + cur));
-        HN_LAUNCH(reset_amax_kernel, dim3(1), dim3(64), 0, st, c->amax, mask);
+        HN_LAUNCH_PDL(c->pdl, reset_amax_kernel, dim3(1), dim3(64), 0, st, c->amax, mask);
         c->launches++;
     }
     // inc
@@ -871,7 +872,7 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
             s2.amax_out = c->amax + S_STATE + 2 * d + nxt;
             s2.H = r;
             s2.W = r;
-            HN_LAUNCH(state2_kernel, dim3((r + S2_TX - 1) / S2_TX, (r + S2_TY - 1) / S2_TY, B), dim3(S2_THREADS), 0, st, s2);
+            HN_LAUNCH_PDL(c->pdl, state2_kernel, dim3((r + S2_TX - 1) / S2_TX, (r + S2_TY - 1) / S2_TY, B), dim3(S2_THREADS), 0, st, s2);
             c->launches++;
         } else {
             Conv3Args t1 = conv_args(c, W.sta[d][1], c->mid2[d], nullptr, c->state[d][nxt], r, S_STATE + 2 * d + nxt);
@@ -938,18 +939,18 @@ static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, co
         const bool fast512 = (n == 512 && c->pml <= 16 && c->spec_fast);
         const bool fast1024 = (n == 1024 && c->pml <= 16 && c->spec_fast);
         if (fast256)
-            HN_LAUNCH(s256::spectral_rows256_kernel, dim3((total_rows + s256::LINES - 1) / s256::LINES), dim3(s256::THREADS), 0, st,
+            HN_LAUNCH_PDL(c->pdl, s256::spectral_rows256_kernel, dim3((total_rows + s256::LINES - 1) / s256::LINES), dim3(s256::THREADS), 0, st,
                       c->spec, reinterpret_cast<const float2*>(u) + off, reinterpret_cast<float2*>(c->rx) + off, total_rows);
         else if (fast512)
-            HN_LAUNCH(s512::spectral_rows512_kernel, dim3((total_rows + s512::LINES - 1) / s512::LINES), dim3(s512::THREADS),
+            HN_LAUNCH_PDL(c->pdl, s512::spectral_rows512_kernel, dim3((total_rows + s512::LINES - 1) / s512::LINES), dim3(s512::THREADS),
                       s512::ROWS_SMEM_BYTES, st, c->spec, reinterpret_cast<const float2*>(u) + off,
                       reinterpret_cast<float2*>(c->rx) + off, total_rows);
         else if (fast1024)
-            HN_LAUNCH(s1024::spectral_rows1024_kernel, dim3((total_rows + s1024::ROWS_LINES - 1) / s1024::ROWS_LINES),
+            HN_LAUNCH_PDL(c->pdl, s1024::spectral_rows1024_kernel, dim3((total_rows + s1024::ROWS_LINES - 1) / s1024::ROWS_LINES),
                       dim3(s1024::ROWS_THREADS), s1024::ROWS_SMEM_BYTES, st, c->spec, reinterpret_cast<const float2*>(u) + off,
                       reinterpret_cast<float2*>(c->rx) + off, total_rows);
         else
-            HN_LAUNCH(spectral_rows_kernel, dim3((total_rows + L - 1) / L), dim3(SPEC_THREADS), spectral_smem_bytes(n, L, c->pml), st,
+            HN_LAUNCH_PDL(c->pdl, spectral_rows_kernel, dim3((total_rows + L - 1) / L), dim3(SPEC_THREADS), spectral_smem_bytes(n, L, c->pml), st,
                       c->spec, reinterpret_cast<const float2*>(u) + off, reinterpret_cast<float2*>(c->rx) + off, total_rows, L);
         ColsArgs a;
         a.u = reinterpret_cast<const float2*>(u) + off;
@@ -965,14 +966,14 @@ static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, co
         a.b0 = b0;
         a.CW = CW;
         if (fast256)
-            HN_LAUNCH(s256::spectral_cols256_kernel, dim3(n / s256::LINES, nb), dim3(s256::THREADS), s256::COLS_SMEM_BYTES, st, c->spec, a);
+            HN_LAUNCH_PDL(c->pdl, s256::spectral_cols256_kernel, dim3(n / s256::LINES, nb), dim3(s256::THREADS), s256::COLS_SMEM_BYTES, st, c->spec, a);
         else if (fast512)
-            HN_LAUNCH(s512::spectral_cols512_kernel, dim3(n / s512::LINES, nb), dim3(s512::THREADS), s512::COLS_SMEM_BYTES, st, c->spec, a);
+            HN_LAUNCH_PDL(c->pdl, s512::spectral_cols512_kernel, dim3(n / s512::LINES, nb), dim3(s512::THREADS), s512::COLS_SMEM_BYTES, st, c->spec, a);
         else if (fast1024)
-            HN_LAUNCH(s1024::spectral_cols1024_kernel, dim3(n / s1024::COLS, nb), dim3(s1024::COLS_THREADS), s1024::COLS_SMEM_BYTES, st,
+            HN_LAUNCH_PDL(c->pdl, s1024::spectral_cols1024_kernel, dim3(n / s1024::COLS, nb), dim3(s1024::COLS_THREADS), s1024::COLS_SMEM_BYTES, st,
                       c->spec, a);
         else
-            HN_LAUNCH(spectral_cols_kernel, dim3((n + CW - 1) / CW, nb), dim3(SPEC_THREADS), spectral_smem_bytes(n, CW, c->pml), st,
+            HN_LAUNCH_PDL(c->pdl, spectral_cols_kernel, dim3((n + CW - 1) / CW, nb), dim3(SPEC_THREADS), spectral_smem_bytes(n, CW, c->pml), st,
                       c->spec, a);
         c->launches += 2;
     }
@@ -982,7 +983,7 @@ static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, co
 static int launch_iteration(hn_ctx* c, int B, cudaStream_t st) {
     HN_TRY(launch_unet(c, B, st, false, false));
     HN_TRY(launch_spectral(c, B, st, c->wf, c->ksq, c->src, c->src_batch, c->res, c->ssq, c->iter_dev, c->amax + S_RES + (c->cur ^ 1)));
-    HN_LAUNCH(advance_iter_kernel, dim3(1), dim3(32), 0, st, c->iter_dev);
+    HN_LAUNCH_PDL(c->pdl, advance_iter_kernel, dim3(1), dim3(32), 0, st, c->iter_dev);
     c->launches++;
     return HN_OK;
 }
@@ -1086,6 +1087,7 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     if (const char* mr = getenv("HELMNET_TC_MIN_RES")) c->tc_min_res = atoi(mr);
     if (const char* mr = getenv("HELMNET_TCR_MIN_RES")) c->tcr_min_res = atoi(mr);
     if (const char* mr = getenv("HELMNET_TCD_MIN_RES")) c->tcd_min_res = atoi(mr);
+    if (const char* pv = getenv("HELMNET_PDL")) c->pdl = atoi(pv) != 0;
     if (const char* en = getenv("HELMNET_ENGINE")) { const int ev = atoi(en); c->engine = ev < 0 ? 0 : ev > 2 ? 2 : ev; }
 #ifndef HN_HAVE_TC
     c->engine = 0;

@@ -104,9 +104,13 @@ __global__ void finalize_rmse_kernel(const double* __restrict__ ssq, float* __re
 // zero the amax slots whose bit is set in `mask` (slots of tensors that are re-produced in this UNet pass)
 __global__ void reset_amax_kernel(unsigned* slots, unsigned long long mask) {
     const int i = threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
     if (i < 64 && ((mask >> i) & 1ull)) slots[i] = 0u;
 }
 __global__ void advance_iter_kernel(int* it) {
+    pdl_wait();
+    pdl_trigger();
     if (threadIdx.x == 0 && blockIdx.x == 0) *it += 1;
 }
 

@@ -200,6 +200,8 @@ __global__ void __launch_bounds__(SPEC_THREADS) spectral_rows_kernel(SpecTables 
     const int row0 = blockIdx.x * L;
     const int nl = min(L, total_rows - row0);
     for (int i = threadIdx.x; i < n; i += blockDim.x) tw[i] = __ldg(t.tw + i);
+    pdl_wait();      // operator tables above; fields written by earlier kernels below (common.cuh: HN_LAUNCH_PDL)
+    pdl_trigger();
     for (int it = threadIdx.x; it < nl * n; it += blockDim.x) {
         const int l = it / n, j = it - l * n;
         A[l * lp + pidx(j)] = __ldg(u + (size_t)(row0 + l) * n + j);
@@ -238,6 +240,8 @@ __global__ void __launch_bounds__(SPEC_THREADS) spectral_cols_kernel(SpecTables 
     const int nc = min(CW, n - j0);
     const size_t img = (size_t)b * n * n;
     for (int i = threadIdx.x; i < n; i += blockDim.x) tw[i] = __ldg(t.tw + i);
+    pdl_wait();      // operator tables above; fields written by earlier kernels below (common.cuh: HN_LAUNCH_PDL)
+    pdl_trigger();
     for (int it = threadIdx.x; it < n * CW; it += blockDim.x) {
         const int i = it / CW, c = it - i * CW;
         if (c < nc) A[c * lp + pidx(i)] = __ldg(a.u + img + (size_t)i * n + j0 + c);

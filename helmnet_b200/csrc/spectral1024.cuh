@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(ROWS_THREADS) spectral_rows1024_kernel(SpecTab
     RowsSmem& sh = *reinterpret_cast<RowsSmem*>(smem_raw);
     load_tab(sh.tab, t);
     __syncthreads();
+    pdl_wait();      // operator tables above; fields written by earlier kernels below (common.cuh: HN_LAUNCH_PDL)
+    pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = lane & 15, g = lane >> 4, s = warp & 1;
     const int row = blockIdx.x * ROWS_LINES + (warp >> 1);
@@ -173,6 +175,8 @@ __global__ void __launch_bounds__(COLS_THREADS) spectral_cols1024_kernel(SpecTab
     ColsSmem& sh = *reinterpret_cast<ColsSmem*>(smem_raw);
     const int b = blockIdx.y, j0 = blockIdx.x * COLS;
     const size_t img = (size_t)b * N * N;
+    pdl_wait();      // common.cuh: HN_LAUNCH_PDL
+    pdl_trigger();
     for (int it = threadIdx.x; it < N * COLS; it += COLS_THREADS) {
         const int i = it >> 3, c = it & 7;
         s256::cp_async8(&sh.tile[i * TILE_P + c], a.u + img + (size_t)i * N + j0 + c);

@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(THREADS) spectral_rows256_kernel(SpecTables t,
     __shared__ float2 tbuf[LINES][TB];
     load_tab(tab, t);
     __syncthreads();
+    pdl_wait();      // operator tables above; fields written by earlier kernels below (common.cuh: HN_LAUNCH_PDL)
+    pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = lane & 15, ll = warp * 2 + (lane >> 4);
     const int row = blockIdx.x * LINES + ll;
@@ -157,6 +159,8 @@ __global__ void __launch_bounds__(THREADS) spectral_cols256_kernel(SpecTables t,
     ColsSmem& sh = *reinterpret_cast<ColsSmem*>(smem_raw);
     const int b = blockIdx.y, j0 = blockIdx.x * LINES;
     const size_t img = (size_t)b * N * N;
+    pdl_wait();      // common.cuh: HN_LAUNCH_PDL
+    pdl_trigger();
     for (int it = threadIdx.x; it < N * LINES; it += THREADS) {
         const int i = it >> 3, c = it & 7;
         cp_async8(&sh.tile[i * TILE_P + c], a.u + img + (size_t)i * N + j0 + c);

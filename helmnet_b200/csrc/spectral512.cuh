@@ -111,6 +111,8 @@ __global__ void __launch_bounds__(THREADS) spectral_rows512_kernel(SpecTables t,
     RowsSmem& sh = *reinterpret_cast<RowsSmem*>(smem_raw);
     load_tab(sh.tab, t);
     __syncthreads();
+    pdl_wait();      // operator tables above; fields written by earlier kernels below (common.cuh: HN_LAUNCH_PDL)
+    pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = lane & 15, g = lane >> 4;
     const int row = blockIdx.x * LINES + warp;
@@ -141,6 +143,8 @@ __global__ void __launch_bounds__(THREADS) spectral_cols512_kernel(SpecTables t,
     ColsSmem& sh = *reinterpret_cast<ColsSmem*>(smem_raw);
     const int b = blockIdx.y, j0 = blockIdx.x * LINES;
     const size_t img = (size_t)b * N * N;
+    pdl_wait();      // common.cuh: HN_LAUNCH_PDL
+    pdl_trigger();
     for (int it = threadIdx.x; it < N * LINES; it += THREADS) {
         const int i = it >> 3, c = it & 7;
         s256::cp_async8(&sh.tile[i * TILE_P + c], a.u + img + (size_t)i * N + j0 + c);
