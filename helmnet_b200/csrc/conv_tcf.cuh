@@ -84,6 +84,7 @@ struct Args {
     const unsigned* amax_in1;
     unsigned* amax_out;
     int* error_flag;
+    int pdl_trig;               // PDL: let the next kernel's CTAs become resident as this grid's CTAs exit (hn_ctx::pdl)
     float sigma_max;
     float w_inv1, w_inv2;       // 2^-kw of the two layers
     float mid_l1, mid_bmax;     // max_co sum |W1[co]|, max |b1|
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
     // everything above touched only this CTA's shared memory / TMEM and the constant weight images: from here on the kernel
     // reads what earlier kernels of the iteration wrote (common.cuh: HN_LAUNCH_PDL)
     pdl_wait();
-    pdl_trigger();
+    if (a.pdl_trig) pdl_trigger();
     // ---- block scales ---------------------------------------------------------------------------------------
     float amax_in;
     if constexpr (SRC == SRC_INC) {

@@ -84,6 +84,7 @@ struct Args {
     const unsigned* amax_in1;   // INC: max|res| slot; others: source B
     unsigned* amax_out;         // EPI_STORE: max|out|; EPI_OUTC: max|updated wavefield|
     int* error_flag;
+    int pdl_trig;               // PDL: let the next kernel's CTAs become resident as this grid's CTAs exit (hn_ctx::pdl)
     float sigma_max;            // INC: max of the sigma profile
     float w_inv_scale;
     int H, W;
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
     // everything above touched only this CTA's shared memory / TMEM and the constant weight images: from here on the kernel
     // reads what earlier kernels of the iteration wrote (common.cuh: HN_LAUNCH_PDL)
     pdl_wait();
-    pdl_trigger();
+    if (a.pdl_trig) pdl_trigger();
     // block scale of the activations (see conv_tc.cuh): x' = x * 2^sa, max|x'| in [2^13, 2^14)
     float amax;
     if constexpr (SRC == SRC_INC) {

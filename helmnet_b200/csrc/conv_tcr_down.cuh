@@ -53,6 +53,7 @@ struct Args {
     const unsigned* amax_in;
     unsigned* amax_out;
     int* error_flag;
+    int pdl_trig;               // PDL: let the next kernel's CTAs become resident as this grid's CTAs exit (hn_ctx::pdl)
     float w_inv_scale;
     int H, W;                   // input resolution
     int nsx, nsy, total_strips;
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
     // everything above touched only this CTA's shared memory / TMEM and the constant weight images: from here on the kernel
     // reads what earlier kernels of the iteration wrote (common.cuh: HN_LAUNCH_PDL)
     pdl_wait();
-    pdl_trigger();
+    if (a.pdl_trig) pdl_trigger();
     const float amax = __uint_as_float(ld_fresh(a.amax_in));
     int e = (int)((__float_as_uint(amax) >> 23) & 0xffu);
     if (e < 40 || e > 250) e = 127;

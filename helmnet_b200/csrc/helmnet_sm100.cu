@@ -108,7 +108,12 @@ struct hn_ctx {
     int tc_min_res = 16;       // use the tensor-core kernels for levels with resolution >= this
     int tcr_min_res = 48;      // row-streaming tensor-core kernel for widths >= this (128-wide strips)
     int num_sms = 148;
-    bool pdl = false;          // programmatic dependent launch for the kernels of an iteration (common.cuh: HN_LAUNCH_PDL)
+    // Programmatic dependent launch for the kernels of an iteration (common.cuh: HN_LAUNCH_PDL).  pdl_mode (HELMNET_PDL):
+    // 0 off; 1 every kernel triggers its dependents early; 2 (default when on) the persistent tcgen05 kernels that run TWO
+    // CTAs per SM do not: CTAs of the next kernel that take over SM slots one by one break the placement (one long + one
+    // short strip list per SM) their static strip assignment is balanced for; 3 no tcgen05 kernel triggers early.
+    bool pdl = false;
+    int pdl_mode = 0;
     int tcd_min_res = 64;      // tensor-core down-/up-sampling for output (input) widths >= this (M = 64 MMAs at exactly 64); 32 works
                                // too (-1 %), but the fp32 CUDA-core kernels keep a wider margin on the README RMSE-trajectory bar
     Weights W;
@@ -537,6 +542,7 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
             t.nsy = (a.H + tcr::ROWS - 1) / tcr::ROWS;
             t.total_strips = t.nsx * t.nsy * B;
             const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;
+            t.pdl_trig = c->pdl_mode == 1;
             HN_LAUNCH_PDL(c->pdl, (tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI_STORE2>), dim3(tgrid), dim3(tcr::THREADS), tcr::smem_bytes(SRC), st, t);
             c->launches++;
             return HN_OK;
@@ -561,6 +567,7 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
             t.nsy = (a.H + tcr::ROWS - 1) / tcr::ROWS;
             t.total_strips = t.nsx * t.nsy * B;
             const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;   // persistent: 2 CTAs per SM
+            t.pdl_trig = c->pdl_mode == 1;
             HN_LAUNCH_PDL(c->pdl, (tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI>), dim3(tgrid), dim3(tcr::THREADS), tcr::smem_bytes(SRC), st, t);
             c->launches++;
             return HN_OK;
@@ -664,6 +671,7 @@ static int launch_down(hn_ctx* c, int d, int B, cudaStream_t st) {
         t.nsy = (r / 2 + tcd::ROWS_O - 1) / tcd::ROWS_O;
         t.total_strips = t.nsx * t.nsy * B;
         const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;
+        t.pdl_trig = c->pdl_mode == 1;
         HN_LAUNCH_PDL(c->pdl, (tcd::down_tcr_kernel), dim3(tgrid), dim3(tcr::THREADS), tcd::SMEM_BYTES, st, t);
         c->launches++;
         return HN_OK;
@@ -723,6 +731,7 @@ static int launch_up(hn_ctx* c, int d, int B, cudaStream_t st) {
         t.nsy = (t.Hi + t.rows_i - 1) / t.rows_i;
         t.total_strips = t.nsx * t.nsy * B;
         const int tgrid = t.total_strips < c->num_sms ? t.total_strips : c->num_sms;   // one CTA per SM (owns all 512 TMEM columns)
+        t.pdl_trig = c->pdl_mode == 1 || c->pdl_mode == 2;   // one CTA per SM
         HN_LAUNCH_PDL(c->pdl, (tcu::up_tcr_kernel), dim3(tgrid), dim3(tcr::THREADS), tcu::SMEM_BYTES, st, t);
         c->launches++;
     } else
@@ -765,6 +774,7 @@ static int launch_dconv_nh(hn_ctx* c, const tcf::Args& t0, int B, cudaStream_t s
     t.spi = (t.H + t.rows - 1) / t.rows;
     t.total_strips = t.spi * B;
     const int grid = t.total_strips < cap ? t.total_strips : cap;
+    t.pdl_trig = c->pdl_mode == 1 || (c->pdl_mode == 2 && NH == 2);   // NH == 2: one CTA per SM
     HN_LAUNCH_PDL(c->pdl, (tcf::dconv_tcf_kernel<SRC, NH, EPI>), dim3(grid), dim3(tcf::threads(NH)), tcf::smem_bytes(SRC, NH), st, t);
     c->launches++;
     return 1;
@@ -1087,7 +1097,8 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     if (const char* mr = getenv("HELMNET_TC_MIN_RES")) c->tc_min_res = atoi(mr);
     if (const char* mr = getenv("HELMNET_TCR_MIN_RES")) c->tcr_min_res = atoi(mr);
     if (const char* mr = getenv("HELMNET_TCD_MIN_RES")) c->tcd_min_res = atoi(mr);
-    if (const char* pv = getenv("HELMNET_PDL")) c->pdl = atoi(pv) != 0;
+    if (const char* pv = getenv("HELMNET_PDL")) c->pdl_mode = atoi(pv);
+    c->pdl = c->pdl_mode != 0;
     if (const char* en = getenv("HELMNET_ENGINE")) { const int ev = atoi(en); c->engine = ev < 0 ? 0 : ev > 2 ? 2 : ev; }
 #ifndef HN_HAVE_TC
     c->engine = 0;
