@@ -109,11 +109,11 @@ struct hn_ctx {
     int tcr_min_res = 48;      // row-streaming tensor-core kernel for widths >= this (128-wide strips)
     int num_sms = 148;
     // Programmatic dependent launch for the kernels of an iteration (common.cuh: HN_LAUNCH_PDL).  pdl_mode (HELMNET_PDL):
-    // 0 off; 1 every kernel triggers its dependents early; 2 (default when on) the persistent tcgen05 kernels that run TWO
-    // CTAs per SM do not: CTAs of the next kernel that take over SM slots one by one break the placement (one long + one
-    // short strip list per SM) their static strip assignment is balanced for; 3 no tcgen05 kernel triggers early.
-    bool pdl = false;
-    int pdl_mode = 0;
+    // 0 off; 1 every kernel triggers its dependents early; 2 (default) the persistent tcgen05 kernels that run several
+    // rounds of strips with TWO CTAs per SM do not (pdl_early()); 3 no tcgen05 kernel triggers early.
+    bool pdl = true;
+    int pdl_mode = 2;
+    int dconv_min_rows = 8;    // shortest strip of the fused DoubleConv kernels (small batches: more, shorter strips fill more SMs)
     int tcd_min_res = 64;      // tensor-core down-/up-sampling for output (input) widths >= this (M = 64 MMAs at exactly 64); 32 works
                                // too (-1 %), but the fp32 CUDA-core kernels keep a wider margin on the README RMSE-trajectory bar
     Weights W;
@@ -512,6 +512,15 @@ static void pack_double_conv(Packer& pk, Cursor& cur, ConvW out[2], int cin, int
 // ------------------------------------------------------------------------------------------------
 // kernel launch helpers
 // ------------------------------------------------------------------------------------------------
+// Should a persistent tcgen05 kernel let its dependents in early (pdl_trigger)?  Mode 2: yes when it runs one CTA per SM or
+// when every CTA has at most one strip (a single round); a kernel that walks several rounds with two CTAs per SM keeps the
+// default CTA placement, which pairs a long and a short strip list on every SM (measured: down[0] 177 -> 186 us otherwise).
+static inline int pdl_early(const hn_ctx* c, int total_strips, int ctas_per_sm) {
+    if (c->pdl_mode == 1) return 1;
+    if (c->pdl_mode == 2) return (ctas_per_sm == 1 || total_strips <= ctas_per_sm * c->num_sms) ? 1 : 0;
+    return 0;
+}
+
 template <int SRC, int COUT, bool PRELU, int EPI>
 static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
     const size_t smem = conv3_smem_bytes(SRC, COUT);
@@ -542,7 +551,7 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
             t.nsy = (a.H + tcr::ROWS - 1) / tcr::ROWS;
             t.total_strips = t.nsx * t.nsy * B;
             const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;
-            t.pdl_trig = c->pdl_mode == 1;
+            t.pdl_trig = pdl_early(c, t.total_strips, 2);
             HN_LAUNCH_PDL(c->pdl, (tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI_STORE2>), dim3(tgrid), dim3(tcr::THREADS), tcr::smem_bytes(SRC), st, t);
             c->launches++;
             return HN_OK;
@@ -567,7 +576,7 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
             t.nsy = (a.H + tcr::ROWS - 1) / tcr::ROWS;
             t.total_strips = t.nsx * t.nsy * B;
             const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;   // persistent: 2 CTAs per SM
-            t.pdl_trig = c->pdl_mode == 1;
+            t.pdl_trig = pdl_early(c, t.total_strips, 2);
             HN_LAUNCH_PDL(c->pdl, (tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI>), dim3(tgrid), dim3(tcr::THREADS), tcr::smem_bytes(SRC), st, t);
             c->launches++;
             return HN_OK;
@@ -671,7 +680,7 @@ static int launch_down(hn_ctx* c, int d, int B, cudaStream_t st) {
         t.nsy = (r / 2 + tcd::ROWS_O - 1) / tcd::ROWS_O;
         t.total_strips = t.nsx * t.nsy * B;
         const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;
-        t.pdl_trig = c->pdl_mode == 1;
+        t.pdl_trig = pdl_early(c, t.total_strips, 2);
         HN_LAUNCH_PDL(c->pdl, (tcd::down_tcr_kernel), dim3(tgrid), dim3(tcr::THREADS), tcd::SMEM_BYTES, st, t);
         c->launches++;
         return HN_OK;
@@ -731,7 +740,7 @@ static int launch_up(hn_ctx* c, int d, int B, cudaStream_t st) {
         t.nsy = (t.Hi + t.rows_i - 1) / t.rows_i;
         t.total_strips = t.nsx * t.nsy * B;
         const int tgrid = t.total_strips < c->num_sms ? t.total_strips : c->num_sms;   // one CTA per SM (owns all 512 TMEM columns)
-        t.pdl_trig = c->pdl_mode == 1 || c->pdl_mode == 2;   // one CTA per SM
+        t.pdl_trig = pdl_early(c, t.total_strips, 1);
         HN_LAUNCH_PDL(c->pdl, (tcu::up_tcr_kernel), dim3(tgrid), dim3(tcr::THREADS), tcu::SMEM_BYTES, st, t);
         c->launches++;
     } else
@@ -747,10 +756,10 @@ static int launch_up(hn_ctx* c, int d, int B, cudaStream_t st) {
 #ifdef HN_HAVE_TC
 // Fused DoubleConv (conv_tcf.cuh) when the engine and the level allow it: full-width rows of 128 or 256 pixels.
 // Returns 1 when launched, 0 when the caller has to fall back to two launches, negative on error.
-static int dconv_rows_per_strip(int H, int B, int cap) {
-    int best = 8;
+static int dconv_rows_per_strip(int H, int B, int cap, int min_rows) {
+    int best = min_rows;
     long long best_cost = -1;
-    for (int rows = 8; rows <= 128 && rows <= H; rows += 2) {
+    for (int rows = min_rows; rows <= 128 && rows <= H; rows += 2) {
         const int spi = (H + rows - 1) / rows;
         const long long total = (long long)spi * B;
         const long long g = total < cap ? total : cap;
@@ -770,11 +779,11 @@ static int launch_dconv_nh(hn_ctx* c, const tcf::Args& t0, int B, cudaStream_t s
     }
     tcf::Args t = t0;
     const int cap = (NH == 2 ? 1 : 2) * c->num_sms;
-    t.rows = dconv_rows_per_strip(t.H, B, cap);
+    t.rows = dconv_rows_per_strip(t.H, B, cap, c->dconv_min_rows);
     t.spi = (t.H + t.rows - 1) / t.rows;
     t.total_strips = t.spi * B;
     const int grid = t.total_strips < cap ? t.total_strips : cap;
-    t.pdl_trig = c->pdl_mode == 1 || (c->pdl_mode == 2 && NH == 2);   // NH == 2: one CTA per SM
+    t.pdl_trig = pdl_early(c, t.total_strips, NH == 2 ? 1 : 2);
     HN_LAUNCH_PDL(c->pdl, (tcf::dconv_tcf_kernel<SRC, NH, EPI>), dim3(grid), dim3(tcf::threads(NH)), tcf::smem_bytes(SRC, NH), st, t);
     c->launches++;
     return 1;
@@ -1098,6 +1107,7 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     if (const char* mr = getenv("HELMNET_TCR_MIN_RES")) c->tcr_min_res = atoi(mr);
     if (const char* mr = getenv("HELMNET_TCD_MIN_RES")) c->tcd_min_res = atoi(mr);
     if (const char* pv = getenv("HELMNET_PDL")) c->pdl_mode = atoi(pv);
+    if (const char* pv = getenv("HELMNET_DCONV_MIN_ROWS")) { const int v = atoi(pv); if (v >= 2 && v % 2 == 0) c->dconv_min_rows = v; }
     c->pdl = c->pdl_mode != 0;
     if (const char* en = getenv("HELMNET_ENGINE")) { const int ev = atoi(en); c->engine = ev < 0 ? 0 : ev > 2 ? 2 : ev; }
 #ifndef HN_HAVE_TC
