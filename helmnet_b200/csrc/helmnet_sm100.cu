@@ -113,7 +113,7 @@ struct hn_ctx {
     // rounds of strips with TWO CTAs per SM do not (pdl_early()); 3 no tcgen05 kernel triggers early.
     bool pdl = true;
     int pdl_mode = 2;
-    int dconv_min_rows = 8;    // shortest strip of the fused DoubleConv kernels (small batches: more, shorter strips fill more SMs)
+    int dconv_min_rows = 4;    // shortest strip of the fused DoubleConv kernels (small batches: more, shorter strips fill more SMs)
     int tcd_min_res = 64;      // tensor-core down-/up-sampling for output (input) widths >= this (M = 64 MMAs at exactly 64); 32 works
                                // too (-1 %), but the fp32 CUDA-core kernels keep a wider margin on the README RMSE-trajectory bar
     Weights W;

@@ -224,3 +224,35 @@ def test_large_amplitude_inputs_stay_in_range(cuda_solver, f_weights):
         assert max(rel_l2(out["wavefields"][k], ref["wavefields"][k]) for k in range(3)) < PER_ITER_TOL
     finally:
         s.hparams.source_amplitude = old
+
+
+@pytest.mark.parametrize("n,b", [(256, 3), (96, 2)])
+def test_launch_scheduling_options_do_not_change_results(_cuda_solver_base, n, b, monkeypatch):
+    """Programmatic dependent launch (HELMNET_PDL modes, common.cuh: HN_LAUNCH_PDL) and the strip height of the fused
+    DoubleConv kernels (HELMNET_DCONV_MIN_ROWS) only change when and where CTAs run: wavefields must be bit-identical to
+    the fully serialised launch order, for the graph-replayed loop of every engine."""
+    s = _cuda_solver_base
+    g = torch.Generator().manual_seed(n)
+    sos = (1.0 + torch.rand(b, 1, n, n, generator=g)).cuda()
+
+    def run(env):
+        for k_, v in env.items():
+            monkeypatch.setenv(k_, v)
+        s._release_ctx()                       # the options are read by hn_create
+        s.set_domain_size(n, source_location=[n // 8, n // 2])
+        out = s.forward(sos, num_iterations=8)
+        s.sync_check()
+        return out["wavefields"][0].clone(), out["residual_rmse"].clone()
+
+    for engine in (1, 2):
+        s.set_engine(engine)
+        ref_wf, ref_rm = run({"HELMNET_PDL": "0", "HELMNET_DCONV_MIN_ROWS": "8"})
+        assert torch.isfinite(ref_wf).all()
+        for env in ({"HELMNET_PDL": "1"}, {"HELMNET_PDL": "2"}, {"HELMNET_PDL": "3"}, {"HELMNET_PDL": "2", "HELMNET_DCONV_MIN_ROWS": "2"},
+                    {"HELMNET_PDL": "1", "HELMNET_DCONV_MIN_ROWS": "4"}):
+            wf, rm = run(env)
+            assert torch.equal(wf, ref_wf), (engine, env)
+            assert rel_l2(rm, ref_rm) < 1e-6, (engine, env)
+    monkeypatch.delenv("HELMNET_PDL", raising=False)
+    monkeypatch.delenv("HELMNET_DCONV_MIN_ROWS", raising=False)
+    s._release_ctx()
