@@ -109,10 +109,14 @@ struct hn_ctx {
     int tcr_min_res = 48;      // row-streaming tensor-core kernel for widths >= this (128-wide strips)
     int num_sms = 148;
     // Programmatic dependent launch for the kernels of an iteration (common.cuh: HN_LAUNCH_PDL).  pdl_mode (HELMNET_PDL):
-    // 0 off; 1 every kernel triggers its dependents early; 2 (default) the persistent tcgen05 kernels that run several
-    // rounds of strips with TWO CTAs per SM do not (pdl_early()); 3 no tcgen05 kernel triggers early.
-    bool pdl = true;
-    int pdl_mode = 2;
+    // 0 off; 1 every kernel triggers its dependents early; 2 the persistent tcgen05 kernels that run several rounds of
+    // strips with TWO CTAs per SM do not (pdl_early()); 3 no tcgen05 kernel triggers early.  Unset (pdl_cfg = -1): mode 2
+    // for solves of at most kPdlAutoPoints points, off above -- measured on B200 (tools/gpu_ab_pdl.sh): 256^2 x 1 -12 %,
+    // 128^2 x 64 -5 %, 96^2 x 32 -3.5 % per iteration, but nothing (+-0.5 %) at 256^2 x 256 / 512^2 x 64 / 1024^2 x 8, where
+    // every kernel runs for 100+ us and the iteration is power-capped.  pdl / pdl_mode are the values in effect (pdl_select).
+    int pdl_cfg = -1;
+    bool pdl = false;
+    int pdl_mode = 0;
     int dconv_min_rows = 4;    // shortest strip of the fused DoubleConv kernels (small batches: more, shorter strips fill more SMs)
     int tcd_min_res = 64;      // tensor-core down-/up-sampling for output (input) widths >= this (M = 64 MMAs at exactly 64); 32 works
                                // too (-1 %), but the fp32 CUDA-core kernels keep a wider margin on the README RMSE-trajectory bar
@@ -512,6 +516,11 @@ static void pack_double_conv(Packer& pk, Cursor& cur, ConvW out[2], int cin, int
 // ------------------------------------------------------------------------------------------------
 // kernel launch helpers
 // ------------------------------------------------------------------------------------------------
+constexpr long long kPdlAutoPoints = 4ll << 20;
+static inline void pdl_select(hn_ctx* c, int B) {
+    c->pdl_mode = c->pdl_cfg >= 0 ? c->pdl_cfg : ((long long)B * c->n * c->n <= kPdlAutoPoints ? 2 : 0);
+    c->pdl = c->pdl_mode != 0;
+}
 // Should a persistent tcgen05 kernel let its dependents in early (pdl_trigger)?  Mode 2: yes when it runs one CTA per SM or
 // when every CTA has at most one strip (a single round); a kernel that walks several rounds with two CTAs per SM keeps the
 // default CTA placement, which pairs a long and a short strip list on every SM (measured: down[0] 177 -> 186 us otherwise).
@@ -838,6 +847,7 @@ static int launch_dconv(hn_ctx* c, const ConvW (&w)[2], const float* inA, const 
 // building it from (wf, 1e3*res, sigmas); `raw_out`: store the network output to c->dwf instead of updating wf.
 static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool raw_out) {
     const Weights& W = c->W;
+    pdl_select(c, B);
     const int cur = c->cur, nxt = cur ^ 1;
     // zero the amax slots of everything this pass (re)produces; keep the current hidden-state slots and in6
     {
@@ -942,6 +952,7 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
 static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, const float* ksq, const float* src,
                            int src_batch, float* res, double* ssq, const int* slot, unsigned* amax_out = nullptr) {
     const int n = c->n;
+    pdl_select(c, B);
     const int L = c->rows_L, CW = c->cols_CW;
     // Row and column passes alternate over chunks of samples small enough that u, rx and k_sq of a chunk stay in the
     // 126 MB L2 between the two kernels (20 B per point), so the column pass re-reads them from L2, not HBM.
@@ -1106,9 +1117,9 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     if (const char* mr = getenv("HELMNET_TC_MIN_RES")) c->tc_min_res = atoi(mr);
     if (const char* mr = getenv("HELMNET_TCR_MIN_RES")) c->tcr_min_res = atoi(mr);
     if (const char* mr = getenv("HELMNET_TCD_MIN_RES")) c->tcd_min_res = atoi(mr);
-    if (const char* pv = getenv("HELMNET_PDL")) c->pdl_mode = atoi(pv);
+    if (const char* pv = getenv("HELMNET_PDL")) c->pdl_cfg = atoi(pv);
     if (const char* pv = getenv("HELMNET_DCONV_MIN_ROWS")) { const int v = atoi(pv); if (v >= 2 && v % 2 == 0) c->dconv_min_rows = v; }
-    c->pdl = c->pdl_mode != 0;
+    pdl_select(c, max_batch);
     if (const char* en = getenv("HELMNET_ENGINE")) { const int ev = atoi(en); c->engine = ev < 0 ? 0 : ev > 2 ? 2 : ev; }
 #ifndef HN_HAVE_TC
     c->engine = 0;
