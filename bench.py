@@ -210,7 +210,7 @@ def run_ours(args):
         st_ms[0] += stage[0] / reps
         st_ms[1] += stage[1] / reps
     # algorithmic HBM bytes per level-0 point and launch: activations are NHWC8 fp32 = 32 B
-    fused = solver._engine >= 2 and n in (64, 128, 256)
+    fused = solver._engine >= 2 and n <= 256 and (n in (32, 64, 128, 256) or os.environ.get("HELMNET_TCF_ANY_WIDTH", "1") != "0")
     if fused:   # engine 2: one kernel per DoubleConv; the intermediate 8-channel tensor never reaches HBM
         kernel_table = [
             (9, "dconv_tcf_kernel<A8_B8,OUTC> (decode[0] 16->8->8 + outc, level 0; reads up 32 + skip 32, writes d_wf 8)", 32 + 32 + 8),

@@ -3,7 +3,7 @@
 //
 // Two chained row-streaming implicit GEMMs (the mapping of conv_tcr.cuh: M = 128 pixels of one image row,
 // vertical taps in N, split-fp16 operands, output-stationary TMEM accumulator rings) inside ONE persistent CTA
-// that owns FULL-WIDTH image rows (W = 128 * NH, NH = 1 or 2; NH = 0 / -1 stand for W = 64 / 32 with M = 64 MMAs, whose
+// that owns FULL-WIDTH image rows (up to W = 128 * NH pixels, NH = 1 or 2; NH = 0 / -1 stand for W = 64 / 32 with M = 64 MMAs, whose
 // accumulator row i sits in TMEM lane 32 (i / 16) + i % 16), so the second convolution finds the left/right
 // neighbours of every intermediate pixel in its own shared memory -- no halo exchange and no recomputation
 // along x; along y a strip of R output rows recomputes 2 intermediate rows.
@@ -88,7 +88,9 @@ struct Args {
     float sigma_max;
     float w_inv1, w_inv2;       // 2^-kw of the two layers
     float mid_l1, mid_bmax;     // max_co sum |W1[co]|, max |b1|
-    int H;                      // image rows (W is 128 * NH)
+    int H;                      // image rows
+    int W;                      // image columns, even, <= wpx(NH): the kernel owns full-width rows; GEMM rows / operand positions
+                                // beyond W stay zero (they are the right-hand zero padding of pixel W - 1)
     int rows;                   // output rows per strip (even)
     int spi;                    // strips per image
     int total_strips;
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + NPB);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int H = a.H;
+    const int H = a.H, Wa = a.W;
 
     // ---- setup ------------------------------------------------------------------------------------------
     if (warp == MMA1_WARP) {
@@ -328,7 +330,8 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
             for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
                 const int b = st / spi, y0 = (st - b * spi) * rows;
                 const int R = min(rows, H - y0), NP1 = (R + 4) / 2;
-                const size_t img = (size_t)b * H * W;
+                const size_t img = (size_t)b * H * Wa;
+                const uint32_t row_tx = (uint32_t)Wa * (uint32_t)(SROW / W);   // bytes one image row brings in
 #pragma unroll 1
                 for (int j = 0; j < NP1; j++, gj++) {
                     const int sidx = gj % NSP;
@@ -339,23 +342,23 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
                         mbar_arrive(stage_full + sidx);
                         continue;
                     }
-                    mbar_arrive_expect_tx(stage_full + sidx, ((uint32_t)v0 + (uint32_t)v1) * (uint32_t)SROW);
+                    mbar_arrive_expect_tx(stage_full + sidx, ((uint32_t)v0 + (uint32_t)v1) * row_tx);
 #pragma unroll
                     for (int t = 0; t < 2; t++) {
                         if (!(t == 0 ? v0 : v1)) continue;
                         uint8_t* dst = stage + (size_t)(sidx * 2 + t) * SROW;
-                        const size_t rowpix = img + (size_t)(gy0 + t) * W;
+                        const size_t rowpix = img + (size_t)(gy0 + t) * Wa;
                         if constexpr (SRC == SRC_INC) {
-                            tma_load_1d(dst, a.inA + rowpix * 2, W * 8, stage_full + sidx);
-                            tma_load_1d(dst + W * 8, a.inB + rowpix * 2, W * 8, stage_full + sidx);
+                            tma_load_1d(dst, a.inA + rowpix * 2, Wa * 8, stage_full + sidx);
+                            tma_load_1d(dst + W * 8, a.inB + rowpix * 2, Wa * 8, stage_full + sidx);
                         } else if constexpr (SRC == SRC_A8) {
-                            tma_load_1d(dst, a.inA + rowpix * 8, W * 32, stage_full + sidx);
+                            tma_load_1d(dst, a.inA + rowpix * 8, Wa * 32, stage_full + sidx);
                         } else if constexpr (SRC == SRC_A8_B8) {
-                            tma_load_1d(dst, a.inA + rowpix * 8, W * 32, stage_full + sidx);
-                            tma_load_1d(dst + W * 32, a.inB + rowpix * 8, W * 32, stage_full + sidx);
+                            tma_load_1d(dst, a.inA + rowpix * 8, Wa * 32, stage_full + sidx);
+                            tma_load_1d(dst + W * 32, a.inB + rowpix * 8, Wa * 32, stage_full + sidx);
                         } else {
-                            tma_load_1d(dst, a.inA + rowpix * 8, W * 32, stage_full + sidx);
-                            tma_load_1d(dst + W * 32, a.inB + rowpix * 2, W * 8, stage_full + sidx);
+                            tma_load_1d(dst, a.inA + rowpix * 8, Wa * 32, stage_full + sidx);
+                            tma_load_1d(dst + W * 32, a.inB + rowpix * 2, Wa * 8, stage_full + sidx);
                         }
                     }
                 }
@@ -365,7 +368,8 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
     } else if (warp < CONV_WARPS) {
         // =============================== converters: thread <-> image column x = tid ================================
         const int x = tid;
-        const float sig_x = SRC == SRC_INC ? __ldg(a.sigma + x) : 0.f;
+        const bool live = x < Wa;     // columns beyond the image keep zero operands
+        const float sig_x = (SRC == SRC_INC && live) ? __ldg(a.sigma + x) : 0.f;
         const int sw16 = ((x >> 2) & 1) * 16;
         int gj = 0;
 #pragma unroll 1
@@ -387,7 +391,7 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
                     for (int c = 0; c < 8; c++) g0[c] = 0.f;
 #pragma unroll
                     for (int c = 0; c < (G == 2 ? 8 : 1); c++) g1[c] = 0.f;
-                    if (gy >= 0 && gy < H) {
+                    if (gy >= 0 && gy < H && live) {
                         const uint8_t* src = stage + (size_t)(sidx * 2 + t) * SROW;
                         if constexpr (SRC == SRC_INC) {
                             const float2 u2 = *reinterpret_cast<const float2*>(src + x * 8);
@@ -507,8 +511,8 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
     } else if (warp < EPI2_WARP0) {
         // =============================== epilogue 1: accumulators -> PReLU -> operand ring A2 ========================
         const int half = (warp - EPI1_WARP0) >> 2, quad = warp & 3;
-        const bool act = NH > 0 || (lane < 16 && quad * 16 < W);      // M = 64: 16 accumulator rows per TMEM lane quadrant
         const int x = NH <= 0 ? quad * 16 + (lane & 15) : half * 128 + quad * 32 + lane;
+        const bool act = (NH > 0 || (lane < 16 && quad * 16 < W)) && x < Wa;   // M = 64: 16 accumulator rows per TMEM lane quadrant
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + ACC1 + (uint32_t)(half * TR * NC);
         int gj = 0, gmp = 0;
 #pragma unroll 1
@@ -559,8 +563,8 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
     } else {
         // =============================== epilogue 2: accumulators -> bias / outc / update -> HBM =====================
         const int half = (warp - EPI2_WARP0) >> 2, quad = warp & 3;
-        const bool act = NH > 0 || (lane < 16 && quad * 16 < W);
         const int x = NH <= 0 ? quad * 16 + (lane & 15) : half * 128 + quad * 32 + lane;
+        const bool act = (NH > 0 || (lane < 16 && quad * 16 < W)) && x < Wa;
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + ACC2 + (uint32_t)(half * TR * NC);
         float lmax = 0.f;
         int gmp = 0, gop = 0;
@@ -568,14 +572,14 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
         for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
             const int b = st / spi, y0 = (st - b * spi) * rows;
             const int R = min(rows, H - y0), NM = (R + 2) / 2;
-            const size_t img = (size_t)b * H * W;
+            const size_t img = (size_t)b * H * Wa;
 #pragma unroll 1
             for (int q = 0; q < R / 2; q++) {
                 const int ya = 2 * q;
                 float2 wfa = make_float2(0.f, 0.f), wfb = wfa;
                 if (EPI == EPI_OUTC && a.dwf_out == nullptr && act) {   // issue the wavefield loads before waiting on the MMAs
-                    wfa = reinterpret_cast<const float2*>(a.wf)[img + (size_t)(y0 + ya) * W + x];
-                    wfb = reinterpret_cast<const float2*>(a.wf)[img + (size_t)(y0 + ya + 1) * W + x];
+                    wfa = reinterpret_cast<const float2*>(a.wf)[img + (size_t)(y0 + ya) * Wa + x];
+                    wfb = reinterpret_cast<const float2*>(a.wf)[img + (size_t)(y0 + ya + 1) * Wa + x];
                 }
                 const int gmd = gmp + q + 1;               // mid pair that completes output rows 2q, 2q+1
                 if (!mbar_wait(c2_done + (gmd & (NDB - 1)), (uint32_t)(gmd / NDB) & 1u)) { ok = false; break; }
@@ -591,7 +595,7 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
 #pragma unroll
                     for (int c = 0; c < 8; c++)
                         o[c] = fmaf(fmaf(__uint_as_float(v[t][8 + c]), 1.f / 2048.f, __uint_as_float(v[t][c])), scale2, a.bias2[c]);
-                    const size_t pix = img + (size_t)(y0 + ya + t) * W + x;
+                    const size_t pix = img + (size_t)(y0 + ya + t) * Wa + x;
                     if (EPI == EPI_STORE) {
 #pragma unroll
                         for (int c = 0; c < 8; c++) lmax = fmaxf(lmax, fabsf(o[c]));

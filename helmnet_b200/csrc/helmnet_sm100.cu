@@ -117,6 +117,8 @@ struct hn_ctx {
     int pdl_cfg = -1;
     bool pdl = false;
     int pdl_mode = 0;
+    bool tcf_any_width = true; // fused DoubleConv kernels for every even width up to 256 (not only 32 / 64 / 128 / 256)
+    int tcf_min_width = 8;
     int dconv_min_rows = 4;    // shortest strip of the fused DoubleConv kernels (small batches: more, shorter strips fill more SMs)
     int tcd_min_res = 64;      // tensor-core down-/up-sampling for output (input) widths >= this (M = 64 MMAs at exactly 64); 32 works
                                // too (-1 %), but the fp32 CUDA-core kernels keep a wider margin on the README RMSE-trajectory bar
@@ -763,7 +765,7 @@ static int launch_up(hn_ctx* c, int d, int B, cudaStream_t st) {
 }
 
 #ifdef HN_HAVE_TC
-// Fused DoubleConv (conv_tcf.cuh) when the engine and the level allow it: full-width rows of 128 or 256 pixels.
+// Fused DoubleConv (conv_tcf.cuh) when the engine and the level allow it: full-width rows of 8 .. 256 pixels.
 // Returns 1 when launched, 0 when the caller has to fall back to two launches, negative on error.
 static int dconv_rows_per_strip(int H, int B, int cap, int min_rows) {
     int best = min_rows;
@@ -800,7 +802,12 @@ static int launch_dconv_nh(hn_ctx* c, const tcf::Args& t0, int B, cudaStream_t s
 template <int SRC, int EPI>
 static int launch_dconv(hn_ctx* c, const ConvW (&w)[2], const float* inA, const float* inB, float* out, int r, int slot_out, int slot_in0,
                         int slot_in1, int B, cudaStream_t st, const ConvW* outc = nullptr, float* wf = nullptr, float* dwf_out = nullptr) {
-    if (c->engine < 2 || (r != 32 && r != 64 && r != 128 && r != 256) || w[0].tcr == (size_t)-1 || w[1].tcr == (size_t)-1 || !c->tcw) return 0;
+    // full-width rows of up to 256 pixels (even width and height); widths other than 32 / 64 / 128 / 256 run on the next larger
+    // variant with the GEMM rows beyond the image left zero (HELMNET_TCF_ANY_WIDTH=0: only the four exact widths)
+    const bool exact = r == 32 || r == 64 || r == 128 || r == 256;
+    if (c->engine < 2 || r > 256 || r < c->tcf_min_width || (r & 1) || (!exact && !c->tcf_any_width) || w[0].tcr == (size_t)-1 ||
+        w[1].tcr == (size_t)-1 || !c->tcw)
+        return 0;
     tcf::Args t;
     memset(&t, 0, sizeof(t));
     t.inA = inA; t.inB = inB; t.sigma = c->sigma1d;
@@ -831,10 +838,11 @@ static int launch_dconv(hn_ctx* c, const ConvW (&w)[2], const float* inA, const 
     t.w_inv1 = w[0].tc_inv; t.w_inv2 = w[1].tc_inv;
     t.mid_l1 = w[0].l1; t.mid_bmax = w[0].bmax;
     t.H = r;
-    if (r == 256) return launch_dconv_nh<SRC, 2, EPI>(c, t, B, st);
-    if (r == 64) return launch_dconv_nh<SRC, 0, EPI>(c, t, B, st);
-    if (r == 32) return launch_dconv_nh<SRC, -1, EPI>(c, t, B, st);
-    return launch_dconv_nh<SRC, 1, EPI>(c, t, B, st);
+    t.W = r;
+    if (r > 128) return launch_dconv_nh<SRC, 2, EPI>(c, t, B, st);
+    if (r > 64) return launch_dconv_nh<SRC, 1, EPI>(c, t, B, st);
+    if (r > 32) return launch_dconv_nh<SRC, 0, EPI>(c, t, B, st);
+    return launch_dconv_nh<SRC, -1, EPI>(c, t, B, st);
 }
 #define HN_TRY_DCONV(var, expr) \
     int var = (expr);           \
@@ -1118,6 +1126,8 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     if (const char* mr = getenv("HELMNET_TCR_MIN_RES")) c->tcr_min_res = atoi(mr);
     if (const char* mr = getenv("HELMNET_TCD_MIN_RES")) c->tcd_min_res = atoi(mr);
     if (const char* pv = getenv("HELMNET_PDL")) c->pdl_cfg = atoi(pv);
+    if (const char* pv = getenv("HELMNET_TCF_ANY_WIDTH")) c->tcf_any_width = atoi(pv) != 0;
+    if (const char* pv = getenv("HELMNET_TCF_MIN_WIDTH")) c->tcf_min_width = atoi(pv);
     if (const char* pv = getenv("HELMNET_DCONV_MIN_ROWS")) { const int v = atoi(pv); if (v >= 2 && v % 2 == 0) c->dconv_min_rows = v; }
     pdl_select(c, max_batch);
     if (const char* en = getenv("HELMNET_ENGINE")) { const int ev = atoi(en); c->engine = ev < 0 ? 0 : ev > 2 ? 2 : ev; }

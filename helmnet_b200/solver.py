@@ -386,7 +386,7 @@ class IterativeSolver(nn.Module):
 
     def set_engine(self, engine: int):
         """0: fp32 CUDA-core convolutions; 1: tcgen05 split-fp16 tensor-core convolutions, one kernel per conv;
-        2 (default): the same with every DoubleConv at 128/256-pixel-wide levels fused into one kernel."""
+        2 (default): the same with every DoubleConv of a level that is 8..256 pixels wide fused into one kernel."""
         self._engine = int(engine)
         if self._ctx is not None:
             self.lib.check(self.lib.hn_set_engine(self._ctx, self._engine), "hn_set_engine")
