@@ -37,7 +37,10 @@ using tcr::tma_load_1d;
 constexpr int ROWS_O = 32;                 // output rows per strip
 constexpr int NC = 16;                     // accumulator columns per output row
 constexpr int SRP = 2;                     // operand ring depth (input row pairs)
-constexpr int NSP = 2;                     // staging ring depth (input row pairs)
+constexpr int NSP = 2;                     // staging ring depth (input row pairs) for images wider than 128 pixels
+constexpr int NSP_MAX = 4;                 // ... and for narrower ones: half-size rows, twice the depth in the same shared memory
+                                           // (the bytes a CTA keeps in flight towards HBM stay the same: at 128 pixels two
+                                           // pairs of 4 KB rows per CTA covered half of the bandwidth-latency product)
 constexpr int NUB = 16;                    // one barrier per accumulator unit (output row)
 constexpr int NDB = 32;                    // input-pair completion barriers
 constexpr int ROW_OP_BYTES = 4 * PS * 16;  // one operand row: [par 0: hi, lo][par 1: hi, lo] x PS entries
@@ -89,12 +92,16 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
     uint64_t* smem_full = bars;                  // [SRP]  2 x 136 converter arrivals
     uint64_t* pair_done = smem_full + SRP;       // [NDB]  tcgen05.commit
     uint64_t* tmem_empty = pair_done + NDB;      // [NUB]  128 epilogue arrivals per output row
-    uint64_t* stage_full = tmem_empty + NUB;     // [NSP]
-    uint64_t* stage_empty = stage_full + NSP;    // [NSP]  2 x 136
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_empty + NSP);
+    uint64_t* stage_full = tmem_empty + NUB;     // [NSP_MAX]
+    uint64_t* stage_empty = stage_full + NSP_MAX;    // [NSP_MAX]  2 x 136
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_empty + NSP_MAX);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = a.H, W = a.W, Wo = W >> 1;
+    // staging ring geometry: rows of up to 132 staged pixels fit half a slot
+    const bool narrow = W <= 128;
+    const int nsp_sh = narrow ? 2 : 1, nsp_mask = (1 << nsp_sh) - 1;       // ring depth 4 or 2 (row pairs)
+    const uint32_t row_st = narrow ? ROW_ST_BYTES / 2 : ROW_ST_BYTES;
 
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "n"(TMEM_COLS));
@@ -105,7 +112,7 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
         for (int i = 0; i < NDB; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(pair_done + i)));
         for (int i = 0; i < NUB; i++)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(tmem_empty + i)), "r"(EPI_WARPS * 32));
-        for (int i = 0; i < NSP; i++) {
+        for (int i = 0; i < NSP_MAX; i++) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(stage_full + i)));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(stage_empty + i)), "r"(2 * PS));
         }
@@ -157,8 +164,8 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
                 const uint32_t rb = (uint32_t)(hi - lo) * 32u;
 #pragma unroll 1
                 for (int j = 0; j < g.NP; j++, gj++) {
-                    const int sidx = gj % NSP;
-                    if (!mbar_wait(stage_empty + sidx, ((uint32_t)(gj / NSP) & 1u) ^ 1u)) { ok = false; break; }
+                    const int sidx = gj & nsp_mask;
+                    if (!mbar_wait(stage_empty + sidx, ((uint32_t)(gj >> nsp_sh) & 1u) ^ 1u)) { ok = false; break; }
                     const int gy0 = 2 * g.oy0 - 3 + 2 * j;
                     const bool v0 = gy0 >= 0 && gy0 < H, v1 = gy0 + 1 >= 0 && gy0 + 1 < H;
                     if (!v0 && !v1) {
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
 #pragma unroll
                     for (int t = 0; t < 2; t++) {
                         if (!(t == 0 ? v0 : v1)) continue;
-                        uint8_t* dst = stage + (size_t)(sidx * 2 + t) * ROW_ST_BYTES;
+                        uint8_t* dst = stage + (size_t)(sidx * 2 + t) * row_st;
                         tma_load_1d(dst + (lo - xb) * 32, a.in + (g.img_in + (size_t)(gy0 + t) * W + lo) * 8, rb, stage_full + sidx);
                     }
                 }
@@ -192,18 +199,18 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
                 const bool oke = (p < PS - 4) && gxe >= 0 && gxe < W, oko = (p < PS - 4) && gxo >= 0 && gxo < W;
 #pragma unroll 1
                 for (int j = 0; j < g.NP; j++, gj++) {
-                    const int sidx = gj % NSP, s = gj % SRP;
+                    const int sidx = gj & nsp_mask, s = gj % SRP;
                     const int gy = 2 * g.oy0 - 3 + 2 * j + team;
                     float ge[8], go_[8];
 #pragma unroll
                     for (int c = 0; c < 8; c++) { ge[c] = 0.f; go_[c] = 0.f; }
-                    if (!mbar_wait(stage_full + sidx, (uint32_t)(gj / NSP) & 1u)) { ok = false; break; }
-                    if (gy >= 0 && gy < H) {
+                    if (!mbar_wait(stage_full + sidx, (uint32_t)(gj >> nsp_sh) & 1u)) { ok = false; break; }
+                    if (gy >= 0 && gy < H && (oke || oko)) {
                         // A thread owns 64 contiguous bytes (even pixel | odd pixel) at a 64-byte stride.  Reading the four
                         // 16-byte chunks in the rotated order (k + p/2) & 3 makes the 8 lanes of a quarter warp hit 8 distinct
                         // bank groups; the rotation by 2 is undone for free by swapping the parity planes at the store below,
                         // the rotation by 1 with one select per value.
-                        const uint8_t* src = stage + (size_t)(sidx * 2 + team) * ROW_ST_BYTES + (size_t)p * 64;
+                        const uint8_t* src = stage + (size_t)(sidx * 2 + team) * row_st + (size_t)p * 64;
                         const float4 l0 = *reinterpret_cast<const float4*>(src + ((rot + 0) & 3) * 16);
                         const float4 l1 = *reinterpret_cast<const float4*>(src + ((rot + 1) & 3) * 16);
                         const float4 l2 = *reinterpret_cast<const float4*>(src + ((rot + 2) & 3) * 16);
