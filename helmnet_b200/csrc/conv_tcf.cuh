@@ -52,7 +52,14 @@ __host__ __device__ constexpr size_t stage_row_bytes(int src, int nh) {
     return (size_t)wpx(nh) * (src == SRC_INC ? 16 : src == SRC_A8 ? 32 : src == SRC_A8_B2 ? 40 : 64);
 }
 // ring depths in row PAIRS
-__host__ __device__ constexpr int nsp(int src, int nh) { return src == SRC_A8_B8 ? 2 : (src == SRC_INC ? 4 : 3); }
+// (staging: the narrow variants have shared memory to spare and one strip per CTA, so their step time is the HBM latency divided
+//  by the number of row pairs in flight: eight pairs instead of two to four)
+#ifndef HN_TCF_NSP_NARROW
+#define HN_TCF_NSP_NARROW 8
+#endif
+__host__ __device__ constexpr int nsp(int src, int nh) {
+    return (nh <= 0 && HN_TCF_NSP_NARROW > 0) ? HN_TCF_NSP_NARROW : (src == SRC_A8_B8 ? 2 : (src == SRC_INC ? 4 : 3));
+}
 __host__ __device__ constexpr int srp1(int src, int nh) { return groups_of(src) == 1 ? 4 : (nh == 2 ? 3 : 2); }
 __host__ __device__ constexpr int srp2(int src, int nh) { return 2; }
 __host__ __device__ constexpr size_t a1_row_bytes(int src, int nh) { return (size_t)groups_of(src) * 2 * psw(nh) * 16; }
