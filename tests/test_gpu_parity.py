@@ -133,9 +133,10 @@ def test_trajectory_source_maps_golden(cuda_solver, gold):
 
 
 @pytest.mark.parametrize("n,b,iters", [(96, 32, 25), (48, 3, 10), (112, 2, 6), (512, 2, 6), (128, 2, 5), (80, 1, 5), (16, 2, 5),
-                                       (1024, 1, 3)])
+                                       (1024, 1, 3), (144, 2, 4), (208, 1, 3), (32, 5, 4)])
 def test_forward_vs_oracle(cuda_solver, f_weights, n, b, iters):
-    """Seeded synthetic maps (config[1] shape 96^2 x 32 included), per-iteration bar at every iteration."""
+    """Seeded synthetic maps (config[1] shape 96^2 x 32 included), per-iteration bar at every iteration.  The sizes cover every
+    variant of the fused DoubleConv kernel at image widths below its GEMM rows (144: 144 / 72 / 36 / 18, 208: 208 / 104 / 52 / 26)."""
     from helmnet_b200.synthetic import synthetic_sos
     from oracle import helmnet_oracle as O
     s = cuda_solver
