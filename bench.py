@@ -181,19 +181,32 @@ def run_ours(args):
     rmse_buf = torch.empty(max(K, W), b_local, device=dev)
     lib.check(lib.hn_run(ctx, W, ptr(rmse_buf), ptr(None), ptr(None), ptr(None), stream()), "hn_run(warmup)")
     barrier()
-    launches0 = lib.hn_launch_count(ctx)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    lib.check(lib.hn_run(ctx, K, ptr(rmse_buf), ptr(None), ptr(None), ptr(None), stream()), "hn_run")
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = lib.hn_launch_count(ctx) - launches0
+    BAD = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown")
+    remeasured = False
+    for attempt in range(2):
+        launches0 = lib.hn_launch_count(ctx)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        e0.record()
+        lib.check(lib.hn_run(ctx, K, ptr(rmse_buf), ptr(None), ptr(None), ptr(None), stream()), "hn_run")
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        launches = lib.hn_launch_count(ctx) - launches0
+        # a run that saw a hardware / thermal slowdown is rejected and measured again, once (sw_power_cap is kept and noted)
+        redo = torch.tensor([1 if (rank == 0 and attempt == 0 and any(r in BAD for r in clocks["reasons"])) else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(redo, op=dist.ReduceOp.MAX)
+        if int(redo.item()) == 0:
+            break
+        remeasured = True
+        time.sleep(2.0)
+    if clocks is not None:
+        clocks["remeasured"] = remeasured
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
