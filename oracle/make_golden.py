@@ -17,6 +17,7 @@ Fixtures written (float32 unless noted):
   traj_n96_b2.npz                      forward(), 40 iterations, 2 synthetic sos maps
   traj_readme_n256.npz                 README lens example, 120 iterations
   traj_srcmap_n64.npz                  examples/simple_scattering.py style source map, 64^2
+  traj_bench_n256_b2.npz               bench.py's workload (first two synthetic 256^2 maps), 12 iterations
 """
 import json
 import os
@@ -48,7 +49,33 @@ def np32(t):
     return t.detach().contiguous().cpu().numpy().astype(np.float32)
 
 
+def bench_workload_fixture(solver):
+    """traj_bench_n256_b2.npz: the first two maps of bench.py's workload (synthetic_sos(.., 256, seed=1), point source [30,128]),
+    12 iterations of the unmodified reference."""
+    n, b, iters = 256, 2, 12
+    with torch.no_grad():
+        solver.hparams.source_location = [30, 128]
+        solver.set_domain_size(n, source_location=[30, 128])
+        sos = synthetic_sos(32, n, seed=1)[:b].contiguous()
+        out = solver.forward(sos, num_iterations=iters, return_wavefields=True)
+        rm = torch.stack([solver.test_loss_function(r) for r in out["residuals"]], 0)
+        keep = [0, iters - 1]
+        np.savez_compressed(
+            os.path.join(OUT, "traj_bench_n256_b2.npz"),
+            sos=np32(sos), rmse=np32(rm), keep=np.array(keep),
+            wavefields=np.stack([np32(out["wavefields"][i]) for i in keep]),
+            source_location=np.array([30, 128]),
+        )
+
+
 def main():
+    if "--only-bench" in sys.argv:      # add the bench-workload fixture without rewriting the others
+        torch.manual_seed(0)
+        np.random.seed(0)
+        torch.set_num_threads(os.cpu_count())
+        bench_workload_fixture(load_solver())
+        print("written", os.path.join(OUT, "traj_bench_n256_b2.npz"))
+        return
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     np.random.seed(0)
@@ -165,6 +192,7 @@ def main():
             sos=sos_map, source=src, rmse=np32(rm), wavefield=np32(out["wavefields"][0]),
             residual=np32(out["residuals"][-1]),
         )
+    bench_workload_fixture(solver)
     print("golden fixtures written to", OUT)
     for fn in sorted(os.listdir(OUT)):
         print(f"  {fn:45s} {os.path.getsize(os.path.join(OUT, fn)) / 1024:8.1f} KB")

@@ -123,6 +123,19 @@ def test_trajectory_readme_golden(cuda_solver, gold):
         assert e < (PER_ITER_TOL if k < 100 else FINAL_TOL), (k, e)
 
 
+def test_trajectory_bench_workload_golden(cuda_solver, gold):
+    """The bench.py workload (synthetic heterogeneous 256^2 maps) against the unmodified reference: one iteration from the
+    common start at the per-iteration bar; after 12 iterations well inside the final-wavefield bar (1e-3)."""
+    g = gold("traj_bench_n256_b2.npz")
+    s = cuda_solver
+    s.set_domain_size(256, source_location=[30, 128])
+    out = s.forward(torch.tensor(g["sos"]).cuda(), num_iterations=12, return_wavefields=True)
+    e0 = rel_l2(out["wavefields"][0], g["wavefields"][0])
+    e11 = rel_l2(out["wavefields"][11], g["wavefields"][1])
+    assert e0 < PER_ITER_TOL and e11 < 1e-4, (e0, e11)
+    assert rel_l2(out["residual_rmse"], g["rmse"]) < 1e-4
+
+
 def test_trajectory_source_maps_golden(cuda_solver, gold):
     g = gold("traj_srcmap_n64.npz")
     s = cuda_solver

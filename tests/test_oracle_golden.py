@@ -45,6 +45,20 @@ def test_trajectory_n96(gold, f_weights):
         assert rel_l2(out["wavefields"][k], g["wavefields"][i]) < 1e-5
 
 
+def test_trajectory_bench_workload(gold, f_weights):
+    """bench.py's workload (first two synthetic 256^2 maps, source [30,128]): the oracle against the unmodified reference,
+    and the fixture against the generator bench.py uses."""
+    from helmnet_b200.synthetic import synthetic_sos
+    g = gold("traj_bench_n256_b2.npz")
+    assert np.array_equal(synthetic_sos(32, 256, seed=1)[:2].numpy(), g["sos"])
+    orc = O.Oracle(f_weights, 256)
+    orc.set_source(O.point_source(256, [30, 128]))
+    out = orc.forward(torch.tensor(g["sos"]), 12, keep_wavefields=True)
+    assert rel_l2(out["rmse"], g["rmse"]) < 1e-5
+    for i, k in enumerate(g["keep"]):
+        assert rel_l2(out["wavefields"][k], g["wavefields"][i]) < 1e-5
+
+
 def test_trajectory_source_maps(gold, f_weights):
     g = gold("traj_srcmap_n64.npz")
     orc = O.Oracle(f_weights, 64)
