@@ -3,14 +3,19 @@
 
     python bench.py --gpus 1 --steps 30 --warmup 5                     # our arm, 1 B200
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference --steps 5 --warmup 1              # the reference's CPU path (oracle port)
+    python bench.py --impl reference --steps 5 --warmup 1              # the reference's own CPU path
 
 A "step" is ONE solver iteration (UNet update + spectral residual + residual norm) over the whole batch.
-Workload (config.workload): 256x256 synthetic heterogeneous sos maps, batch 256 per GPU, point source at
-[30,128], jcp_paper weights (the slim re-save of the shipped checkpoint in tests/golden).
+Workload (config.workload): BASELINE.json configs[2] -- 256 distinct 256x256 synthetic heterogeneous sos maps
+(SURVEY.md 8(d) recipe, helmnet_b200.synthetic.config_sos("C3")), point source at [30,128], jcp_paper weights (the slim
+re-save of the shipped checkpoint in tests/golden).  The batch of 256 is SHARDED over the N GPUs (256/128/64/32 maps per
+GPU): "scaling": "strong".  `--scaling weak` keeps 256 maps per GPU instead; with N > 1 the weak number
+is measured as well and reported under `weak_scaling`.
 Metric: Mpoint-iterations/s = batch * N^2 * steps / seconds, aggregated over all ranks.
-  value : hn_run timed with CUDA events on the launch stream, all inputs resident in HBM.
-  e2e   : IterativeSolver.forward() from pinned HOST sos maps to pinned HOST wavefield + rmse history.
+  value     : hn_run timed with CUDA events on the launch stream, all inputs resident in HBM (burst: `steps` iterations).
+  sustained : the same over the configuration's full 1000 iterations (power-capped steady state).
+  e2e       : IterativeSolver.forward() from pinned HOST sos maps to pinned HOST wavefields + rmse history
+              (N > 1: + NCCL gather of wavefields and histories on rank 0).
 """
 from __future__ import annotations
 
@@ -30,6 +35,8 @@ CKPT = os.path.join(GOLD, "jcp_paper_trained_weights_slim.ckpt")
 FLOP_PER_POINT = 16103.25          # 2 x 8051.625 MAC, dense count, per point-iteration
 BYTES_PER_POINT_SPECTRAL = 36.0    # read wf 8 (updated in place by the UNet epilogue: d_wf never
 #                                    exists in HBM) ... see DESIGN.md; broadcast source
+CONFIG_OF_N = {96: "C2", 256: "C3", 512: "C4", 1024: "C5"}
+SOURCE_OF_N = {96: [82, 48], 256: [30, 128], 512: [450, 256], 1024: [60, 512]}
 
 
 def load_peaks():
@@ -40,6 +47,25 @@ def load_peaks():
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
                 "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def workload_config(n: int, batch_total: int, world: int, scaling: str):
+    """The `config` object: identical for our arm and the reference arm."""
+    cname = CONFIG_OF_N.get(n, "custom")
+    per = batch_total // world
+    return {"workload": f"{n}x{n} synthetic heterogeneous sos maps (SURVEY 8d recipe {cname}: outline of _make_ellipsoid"
+                        f"{' + smooth heterogeneity' if cname in ('C3', 'C5') else ''}), batch {batch_total} total, "
+                        f"point source {SOURCE_OF_N.get(n, [n // 8, n // 2])}, jcp_paper weights",
+            "n": n, "global_batch": batch_total, "batch_per_gpu": per, "scaling": scaling,
+            "parallelism": f"batch-sharded x{world}, no in-loop collective"}
+
+
+def make_maps(n: int, count: int, start: int = 0):
+    """Maps start .. start+count-1 of the configuration that has domain size n (8(d) recipe); other sizes: generic test maps."""
+    from helmnet_b200.synthetic import config_sos, synthetic_sos
+    if n in CONFIG_OF_N:
+        return config_sos(CONFIG_OF_N[n], count, start=start)
+    return synthetic_sos(start + count, n, seed=1)[start:]
 
 
 class ClockSampler:
@@ -73,7 +99,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, pw, reasons = [], None, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             parts = [p.strip() for p in r.split(",")]
@@ -82,29 +108,92 @@ class ClockSampler:
             try:
                 sm.append(float(parts[0]))
                 mx = float(parts[1])
+                pw.append(float(parts[2]))
             except ValueError:
                 continue
             for nme, v in zip(names, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(pw) if pw else None}
 
 
-def cpu_port_throughput(n: int, batch: int, iters: int, warmup: int, threads: int):
-    """The reference's CPU PyTorch path, restated (oracle/helmnet_oracle.py), timed on the host cores."""
+# ----------------------------------------------------------------------------------------------------------------------
+# the reference itself (unmodified helmnet package: baseline/_ref from `pip install --target`, else /root/reference) through
+# the three import stubs of oracle/_stubs.  Test / baseline infrastructure: only the reference arm and the *_baseline keys use it.
+# ----------------------------------------------------------------------------------------------------------------------
+def reference_tree():
+    cands = [os.environ.get("HELMNET_REFERENCE", "/root/reference")]
+    if os.environ.get("HELMNET_BENCH_IGNORE_BASELINE_REF", "0") != "1":
+        cands.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+    for cand in cands:
+        if cand and os.path.isdir(os.path.join(cand, "helmnet")):
+            return cand
+    return None
+
+
+def load_reference_solver(n: int, device="cpu"):
+    """The UNMODIFIED reference IterativeSolver, or None when the reference package is not on this box."""
+    tree = reference_tree()
+    if tree is None:
+        return None
+    stubs = os.path.join(ROOT, "oracle", "_stubs")
+    for p in (tree, stubs):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    from helmnet import IterativeSolver as RefSolver
+    s = RefSolver.load_from_checkpoint(CKPT, strict=False, test_data_path=None)
+    s.freeze()
+    loc = SOURCE_OF_N.get(n, [n // 8, n // 2])
+    s.hparams.source_location = list(loc)
+    s.to(device)
+    with torch.no_grad():
+        s.set_domain_size(n, source_location=list(loc))
+    return s
+
+
+def reference_throughput(n: int, batch: int, iters: int, warmup: int, threads: int, device="cpu"):
+    """(Mpoint-it/s, ms/iteration, kind) of the reference's own forward() on `device` (CPU: all host threads; CUDA: eager
+    PyTorch = cuDNN + cuFFT with TF32 off).  kind = "reference" (unmodified package) or "port" (oracle/helmnet_oracle.py)."""
     import torch
 
-    from helmnet_b200.checkpoint import load_checkpoint
-    from helmnet_b200.synthetic import synthetic_sos
-    from oracle.helmnet_oracle import Oracle, point_source, rmse, zero_states
+    sos = make_maps(n, batch)
+    is_cuda = str(device).startswith("cuda")
+    if not is_cuda:
+        torch.set_num_threads(threads)
+    ref = load_reference_solver(n, device)
+    if ref is not None:
+        sos_d = sos.to(device)
 
-    torch.set_num_threads(threads)
+        def sync():
+            if is_cuda:
+                torch.cuda.synchronize()
+
+        with torch.no_grad():
+            # forward() = get_initials + clear_states + first residual + K x single_step (hybridnet.py:654-697); its per-iteration
+            # cost is constant, so time the loop body directly from the state forward() starts in
+            k_sq, wf = ref.get_initials(sos_d)
+            ref.f.clear_states(wf)
+            res = ref.get_residual(wf, k_sq)
+            for _ in range(warmup):
+                wf, res = ref.single_step(wf, k_sq, res)
+            sync()
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                wf, res = ref.single_step(wf, k_sq, res)
+                _ = ref.test_loss_function(res)
+            sync()
+            dt = time.perf_counter() - t0
+        return batch * n * n * iters / dt / 1e6, dt / iters * 1e3, "reference"
+    if is_cuda:
+        return None, None, "unavailable"
+    from helmnet_b200.checkpoint import load_checkpoint
+    from oracle.helmnet_oracle import Oracle, point_source, rmse, zero_states
     sd = load_checkpoint(CKPT)["state_dict"]
-    w = {k[2:]: v for k, v in sd.items() if k.startswith("f.")}
-    orc = Oracle(w, n)
-    orc.set_source(point_source(n, [30, n // 2]))
-    sos = synthetic_sos(batch, n, seed=1)
+    orc = Oracle({k[2:]: v for k, v in sd.items() if k.startswith("f.")}, n)
+    orc.set_source(point_source(n, SOURCE_OF_N.get(n, [n // 8, n // 2])))
     k_sq, wf = orc.get_initials(sos)
     states = zero_states(batch, n)
     res = orc.residual(wf, k_sq)
@@ -115,37 +204,42 @@ def cpu_port_throughput(n: int, batch: int, iters: int, warmup: int, threads: in
         wf, res, states = orc.single_step(wf, k_sq, res, states)
         _ = rmse(res)
     dt = time.perf_counter() - t0
-    return batch * n * n * iters / dt / 1e6, dt / iters * 1e3
+    return batch * n * n * iters / dt / 1e6, dt / iters * 1e3, "port"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     threads = os.cpu_count() or 1
     n, b = args.n, args.cpu_batch
-    val, ms = cpu_port_throughput(n, b, args.steps, args.warmup, threads)
+    val, ms, kind = reference_throughput(n, b, args.steps, args.warmup, threads)
+    sample = (f"{n}x{n}, first {b} maps of the workload per step (bounded sample; work per map and iteration is constant), "
+              f"{args.steps} iterations after {args.warmup} warm-up, torch CPU fp32, {threads} threads, "
+              + ("the unmodified reference package (IterativeSolver.single_step loop of forward())" if kind == "reference"
+                 else "oracle/helmnet_oracle.py port (reference package not on this box)"))
     line = {
         "impl": "reference", "metric": "Mpoint-iterations/s", "value": val, "unit": "Mpoint-iterations/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{n}x{n} synthetic sos, batch {args.batch} per GPU (reference arm: bounded sample, batch {b} per step)",
-                   "n": n, "batch_per_gpu": args.batch},
-        "cpu_baseline": {"value": val, "unit": "Mpoint-iterations/s", "cores": threads, "kind": "port",
-                         "sample": f"{n}x{n}, batch {b}, {args.steps} iterations after {args.warmup} warm-up, torch CPU fp32"},
+        "config": workload_config(n, args.batch if args.scaling == "strong" else args.batch * world, world, args.scaling),
+        "cpu_baseline": {"value": val, "unit": "Mpoint-iterations/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "Mpoint-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
+# ----------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
     from helmnet_b200 import IterativeSolver
-    from helmnet_b200.sharding import gather_results
-    from helmnet_b200.synthetic import synthetic_sos
+    from helmnet_b200.sharding import gather_results, shard_sizes, shard_slice
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -157,31 +251,52 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n, K, W = args.n, args.steps, args.warmup
-    b_local = args.batch if args.scaling == "weak" else args.batch // world
-    b_total = b_local * world
+    if args.scaling == "strong":
+        b_total = args.batch
+        lo, hi = shard_slice(b_total, world, rank)
+        sizes = shard_sizes(b_total, world)
+    else:
+        b_total = args.batch * world
+        lo, hi = rank * args.batch, (rank + 1) * args.batch
+        sizes = [args.batch] * world
+    b_local = hi - lo
+    if b_local < 1:
+        raise SystemExit("bench.py: fewer maps than GPUs")
 
     solver = IterativeSolver.load_from_checkpoint(CKPT, strict=False, test_data_path=None)
     solver.freeze()
     solver.to(dev)
-    solver.set_domain_size(n, source_location=[30, n // 2])
-    # distinct maps per rank; 32 distinct maps tiled over the batch keep host generation short
-    base = synthetic_sos(min(b_local, 32), n, seed=1 + rank)
-    sos_host = base.repeat((b_local + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:b_local].contiguous().pin_memory()
+    solver.set_domain_size(n, source_location=SOURCE_OF_N.get(n, [n // 8, n // 2]))
+    sos_host = make_maps(n, b_local, start=lo).contiguous().pin_memory()      # this rank's slice: distinct maps
     sos_dev = sos_host.to(dev, non_blocking=True)
     lib, ptr, stream = solver.lib, solver._ptr, solver._stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_run(ctx, iters, rmse_buf):
+        """`iters` iterations of hn_run, device-timed on the launch stream, max over ranks (ms)."""
+        barrier()
+        e0.record()
+        lib.check(lib.hn_run(ctx, iters, ptr(rmse_buf), ptr(None), ptr(None), ptr(None), stream()), "hn_run")
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
     # ---------------- device-resident timing: `value` ------------------------------------------------
     ctx = solver._ensure_ctx(b_local)
     lib.check(lib.hn_reset(ctx, ptr(sos_dev), b_local, stream()), "hn_reset")
-    rmse_buf = torch.empty(max(K, W), b_local, device=dev)
+    rmse_buf = torch.empty(max(K, W, 1), b_local, device=dev)
     lib.check(lib.hn_run(ctx, W, ptr(rmse_buf), ptr(None), ptr(None), ptr(None), stream()), "hn_run(warmup)")
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     BAD = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown")
     remeasured = False
     for attempt in range(2):
@@ -189,12 +304,7 @@ def run_ours(args):
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        barrier()
-        e0.record()
-        lib.check(lib.hn_run(ctx, K, ptr(rmse_buf), ptr(None), ptr(None), ptr(None), stream()), "hn_run")
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
+        ms_max = timed_run(ctx, K, rmse_buf)
         clocks = sampler.stop() if rank == 0 else None
         launches = lib.hn_launch_count(ctx) - launches0
         # a run that saw a hardware / thermal slowdown is rejected and measured again, once (sw_power_cap is kept and noted)
@@ -207,14 +317,10 @@ def run_ours(args):
         time.sleep(2.0)
     if clocks is not None:
         clocks["remeasured"] = remeasured
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
     value = b_total * n * n * K / (ms_max * 1e-3) / 1e6
+    final_rmse_max = float(rmse_buf[K - 1].max().item())
 
     # ---------------- per-stage and per-kernel device time (CUDA events on the launch stream) -------------
-    import ctypes as C
     stage = (C.c_float * 2)()
     st_ms = [0.0, 0.0]
     reps = 5
@@ -226,7 +332,8 @@ def run_ours(args):
     fused = solver._engine >= 2 and n <= 256 and (n in (32, 64, 128, 256) or os.environ.get("HELMNET_TCF_ANY_WIDTH", "1") != "0")
     if fused:   # engine 2: one kernel per DoubleConv; the intermediate 8-channel tensor never reaches HBM
         kernel_table = [
-            (9, "dconv_tcf_kernel<A8_B8,OUTC> (decode[0] 16->8->8 + outc, level 0; reads up 32 + skip 32, writes d_wf 8)", 32 + 32 + 8),
+            (9, "dconv_tcf_kernel<A8_B8,OUTC> (decode[0] 16->8->8 + outc, level 0; as profiled: reads up 32 + skip 32, writes d_wf 8; "
+                "inside the iteration it reads and rewrites wf instead: 80 B)", 32 + 32 + 8),
             (7, "dconv_tcf_kernel<A8_B2,STORE> (enc[0].conv_signal 10->8->8, level 0)", 32 + 8 + 32),
             (8, "dconv_tcf_kernel<A8_B2,STORE2> (enc[0].conv_state 10->2->2, level 0)", 32 + 8 + 8),
             (6, "dconv_tcf_kernel<INC,STORE> (inc 6->8->8, level 0; reads wf 8 + res 8)", 8 + 8 + 32),
@@ -252,15 +359,20 @@ def run_ours(args):
 
     # ---------------- end to end through the public API: `e2e` ----------------------------------------
     wf_host = torch.empty(b_local, 2, n, n).pin_memory()
-    rm_host = torch.empty(K, b_local).pin_memory()
+    rm_host = torch.empty(K, b_total if rank == 0 else b_local).pin_memory()
 
     def solve_e2e():
         out = solver.forward(sos_host.to(dev, non_blocking=True), num_iterations=K, return_residuals=False)
         wf, rm = out["wavefields"][0], out["residual_rmse"]
-        if world > 1:   # NCCL only gathers results and residual histories
-            gathered = gather_results(wf, rm, dst=0)
+        # every rank reads its own wavefield slice back over its own PCIe link; NCCL gathers the wavefields and the residual
+        # histories on rank 0's device in ONE collective, rank 0 reads the gathered histories back
         wf_host.copy_(wf, non_blocking=True)
-        rm_host.copy_(rm, non_blocking=True)
+        if world > 1:
+            gathered = gather_results(wf, rm, dst=0, sizes=sizes)
+            if rank == 0:
+                rm_host.copy_(gathered[1], non_blocking=True)
+        else:
+            rm_host.copy_(rm, non_blocking=True)
 
     with torch.no_grad():
         solve_e2e()   # warm-up (allocations, graph already built)
@@ -269,18 +381,27 @@ def run_ours(args):
         solve_e2e()
         e1.record()
         barrier()
-    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    e2e_val = b_total * n * n * K / (float(ms_e2e.item()) * 1e-3) / 1e6
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_val = b_total * n * n * K / (ms_e2e * 1e-3) / 1e6
     h2d = b_local * n * n * 4 / K
-    d2h = (b_local * 2 * n * n * 4 + K * b_local * 4) / K
+    d2h = (b_local * 2 * n * n * 4 + K * (b_total if rank == 0 else b_local) * 4) / K
 
-    # ---------------- BASELINE.json's second figure: wall time until every sample's residual RMSE < 1e-3 ----------
-    ttr = None
+    # ---------------- sustained throughput + BASELINE.json's second figure (time until every residual RMSE < 1e-3) ----------
+    ttr, sustained = None, None
     if args.residual_iters > 0:
         with torch.no_grad():
-            hist = solver.forward(sos_dev, num_iterations=args.residual_iters, return_residuals=False)["residual_rmse"]
+            KR = args.residual_iters
+            hist = torch.empty(KR, b_local, device=dev)
+            lib.check(lib.hn_reset(ctx, ptr(sos_dev), b_local, stream()), "hn_reset")
+            sam = ClockSampler(local)
+            if rank == 0:
+                sam.start()
+            ms_long = timed_run(ctx, KR, hist)
+            ck = sam.stop() if rank == 0 else None
+            sustained = {"value": b_total * n * n * KR / (ms_long * 1e-3) / 1e6, "unit": "Mpoint-iterations/s", "iterations": KR,
+                         "ms_per_step": ms_long / KR, "clocks": ck,
+                         "note": "hn_run over the configuration's full iteration count (device-timed, max over ranks): the board "
+                                 "sits at its power cap here, the `value` run is too short to reach it"}
             below = (hist.max(dim=1).values < 1e-3).nonzero()
             k_star = int(below[0].item()) if below.numel() else -1
             kk = torch.tensor([k_star], device=dev)
@@ -296,20 +417,52 @@ def run_ours(args):
                 wf_host.copy_(out["wavefields"][0], non_blocking=True)
                 e1.record()
                 barrier()
-                t_res = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-                if world > 1:
-                    dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
-                ttr = {"reached": True, "iteration_index": k_all, "ms": float(t_res.item()),
+                ttr = {"reached": True, "iteration_index": k_all, "ms": max_over_ranks(e0.elapsed_time(e1)),
                        "definition": "forward() from host sos until max over the batch of test_loss_function RMSE < 1e-3, incl. H2D/D2H"}
             else:
-                ttr = {"reached": False, "iteration_index": None, "ms": None, "iterations_tried": args.residual_iters}
-            # per-sample view (this rank): the reference network itself does not bring every out-of-distribution map below
-            # 1e-3 within the cap (oracle run of the same maps: transient excursions of the residual, then slow decay)
+                ttr = {"reached": False, "iteration_index": None, "ms": None, "iterations_tried": KR,
+                       "note": "the reference network itself leaves some of these out-of-distribution maps above 1e-3 (verified on the "
+                               "unmodified reference, DESIGN.md 4.6); per-sample statistics below"}
             first = (hist < 1e-3).float().argmax(dim=0)
             ok_s = (hist < 1e-3).any(dim=0)
             ttr["samples_reached_frac"] = float(ok_s.float().mean().item())
             ttr["median_iteration_index_of_reached"] = int(first[ok_s].median().item()) if bool(ok_s.any()) else None
-            ttr["ms_per_iteration"] = ms_max / K
+            ttr["ms_per_iteration"] = ms_long / KR
+
+    # ---------------- weak scaling next to the strong headline (N > 1), per-GPU shares of the other configurations ------------
+    def quick_config(nn, per_gpu, iters, wu=3):
+        """ms/iteration of `per_gpu` maps of the configuration with domain size nn on every rank (own context)."""
+        s2 = IterativeSolver.load_from_checkpoint(CKPT, strict=False, test_data_path=None)
+        s2.freeze()
+        s2.to(dev)
+        s2.set_domain_size(nn, source_location=SOURCE_OF_N.get(nn, [nn // 8, nn // 2]))
+        maps = make_maps(nn, per_gpu, start=rank * per_gpu).to(dev)
+        c2 = s2._ensure_ctx(per_gpu)
+        buf = torch.empty(max(iters, wu), per_gpu, device=dev)
+        lib.check(lib.hn_reset(c2, ptr(maps), per_gpu, stream()), "hn_reset")
+        lib.check(lib.hn_run(c2, wu, ptr(buf), ptr(None), ptr(None), ptr(None), stream()), "hn_run")
+        ms_ = timed_run(c2, iters, buf)
+        kpi = int(lib.hn_kernels_per_iteration(c2))
+        s2._release_ctx()
+        del s2, maps, buf
+        torch.cuda.empty_cache()
+        return {"n": nn, "batch_per_gpu": per_gpu, "global_batch": per_gpu * world, "ms_per_step": ms_ / iters,
+                "value": per_gpu * world * nn * nn * iters / (ms_ * 1e-3) / 1e6, "kernels_per_iteration": kpi}
+
+    weak, others = None, None
+    if not args.no_extras:
+        solver._release_ctx()
+        torch.cuda.empty_cache()
+        if world > 1 and args.scaling == "strong" and n == 256:
+            w_ = quick_config(256, args.batch, K, W)
+            weak = {"value": w_["value"], "unit": "Mpoint-iterations/s", "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+                    "ms_per_step": w_["ms_per_step"], "steps": K}
+        if n == 256:
+            others = {"C4_512x512_share_of_batch64_over_8gpus": quick_config(512, 8, 20),
+                      "C5_1024x1024_share_of_batch8_over_8gpus": quick_config(1024, 1, 20)}
+            if world == 1:
+                others["C2_96x96_batch32"] = quick_config(96, 32, 50)
+                others["C3_256x256_share_of_batch256_over_8gpus"] = quick_config(256, 32, 50)
 
     # ---------------- config[0] of BASELINE.json: the README lens (one 256x256 map), time until RMSE < 1e-3 ------------
     readme = None
@@ -333,22 +486,23 @@ def run_ours(args):
                 readme = {"iteration_index": k1, "ms": e0.elapsed_time(e1), "batch": 1,
                           "definition": "README.md:62-70 example: forward() from the host sos map until RMSE < 1e-3, wavefield back on the host"}
                 if not args.no_cpu_baseline:
-                    # the same solve on the reference's CPU path (oracle port), all host cores
-                    from helmnet_b200.checkpoint import load_checkpoint
-                    from oracle.helmnet_oracle import Oracle, point_source, zero_states
+                    # the same solve on the reference's CPU path, all host cores
                     torch.set_num_threads(os.cpu_count() or 1)
-                    sd = load_checkpoint(CKPT)["state_dict"]
-                    orc = Oracle({k[2:]: v for k, v in sd.items() if k.startswith("f.")}, n)
-                    orc.set_source(point_source(n, [30, n // 2]))
+                    ref = load_reference_solver(n, "cpu")
                     t0 = time.perf_counter()
-                    k_sq, wf = orc.get_initials(torch.from_numpy(lens)[None, None])
-                    st_, rs = zero_states(1, n), None
-                    rs = orc.residual(wf, k_sq)
-                    for _ in range(k1 + 1):
-                        wf, rs, st_ = orc.single_step(wf, k_sq, rs, st_)
-                    readme["cpu_port_ms"] = (time.perf_counter() - t0) * 1e3
+                    if ref is not None:
+                        ref.forward(torch.from_numpy(lens)[None, None], num_iterations=k1 + 1)
+                        readme["cpu_kind"] = "reference"
+                    else:
+                        from helmnet_b200.checkpoint import load_checkpoint
+                        from oracle.helmnet_oracle import Oracle, point_source
+                        sd = load_checkpoint(CKPT)["state_dict"]
+                        orc = Oracle({k[2:]: v for k, v in sd.items() if k.startswith("f.")}, n)
+                        orc.set_source(point_source(n, [30, n // 2]))
+                        orc.forward(torch.from_numpy(lens)[None, None], k1 + 1)
+                        readme["cpu_kind"] = "port"
+                    readme["cpu_ms"] = (time.perf_counter() - t0) * 1e3
                     readme["cpu_cores"] = os.cpu_count() or 1
-        # the solver goes back to the benchmark batch lazily (next forward) -- nothing else runs after this point
 
     if rank == 0:
         peaks = load_peaks()
@@ -358,57 +512,88 @@ def run_ours(args):
         ach_tf = FLOP_PER_POINT * pts / t_unet / 1e12 if t_unet > 0 else 0.0
         ach_gb = BYTES_PER_POINT_SPECTRAL * pts / t_spec / 1e9 if t_spec > 0 else 0.0
         # DRAM bytes per launch from the committed ncu capture of this very configuration (null for any other)
-        traffic = {}
-        tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                tj = json.load(f)
-            if tj["config"] == {"n": n, "batch_per_gpu": b_local} and fused:
-                traffic = {int(k): v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tj["kernels"].items()}
+        traffic, traffic_source = {}, None
+        for fn in ("r2_dram_traffic.json", "r1_dram_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", fn)
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    tj = json.load(f)
+                if tj["config"] == {"n": n, "batch_per_gpu": b_local} and fused:
+                    traffic = {int(k): v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tj["kernels"].items()}
+                    traffic_source = f"profiles/{fn}: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this " \
+                                     "configuration (committed file, not measured in this run)"
+                break
         roof = []
         for which, name, bpp in kernel_table:
             ms_k = kern_ms[which]
             gbs = bpp * pts / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
             roof.append({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                         "traffic": traffic.get(which), "algorithmic_bytes": bpp * pts, "kernel": name, "ms_per_launch": ms_k, "algorithmic_bytes_per_point": bpp,
+                         "traffic": traffic.get(which), "traffic_source": traffic_source if which in traffic else None,
+                         "algorithmic_bytes": bpp * pts, "kernel": name, "ms_per_launch": ms_k,
+                         "algorithmic_bytes_per_point": bpp,
                          "peak_source": f"{peaks['source']} (MEASURED_PEAKS.json hbm_gbs, burst copy)"})
-        cpu = None
+        cpu, gpu_eager = None, None
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, _ = cpu_port_throughput(n, args.cpu_batch, args.cpu_iters, 2, threads)
-            cpu = {"value": v, "unit": "Mpoint-iterations/s", "cores": threads, "kind": "port",
-                   "sample": f"{n}x{n}, batch {args.cpu_batch}, {args.cpu_iters} iterations after 2 warm-up, torch CPU fp32 "
-                             "(oracle/helmnet_oracle.py)"}
+            v, ms_c, kind = reference_throughput(n, args.cpu_batch, args.cpu_iters, 2, threads)
+            cpu = {"value": v, "unit": "Mpoint-iterations/s", "cores": threads, "kind": kind, "ms_per_step": ms_c,
+                   "sample": f"{n}x{n}, first {args.cpu_batch} maps of the workload, {args.cpu_iters} iterations after 2 warm-up, torch CPU fp32 ("
+                             + ("unmodified reference package, single_step loop of forward()" if kind == "reference" else "oracle/helmnet_oracle.py port") + ")"}
+        if not args.no_gpu_baseline and world == 1:
+            # secondary baseline: the reference itself in eager PyTorch on this B200 -- cuDNN + cuFFT, TF32 off
+            tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.benchmark = True          # train.py:49
+            try:
+                torch.cuda.empty_cache()
+                gb = min(b_local, args.gpu_baseline_batch)
+                v, ms_g, kind = reference_throughput(n, gb, 10, 3, 1, device=dev)
+                if v is not None:
+                    gpu_eager = {"value": v, "unit": "Mpoint-iterations/s", "kind": kind, "ms_per_step": ms_g, "batch": gb,
+                                 "sample": f"{n}x{n}, first {gb} maps of the workload, 10 iterations after 3 warm-up, the unmodified reference "
+                                           "in eager PyTorch on cuda:0 (cuDNN + cuFFT), allow_tf32=False, cudnn.benchmark=True",
+                                 "speedup_of_value": value / v}
+            except Exception as ex:   # never let the baseline break the bench line
+                gpu_eager = {"value": None, "error": repr(ex)[:300]}
+            finally:
+                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = tf
+        cfg = workload_config(n, b_total, world, args.scaling)
+        cfg.update({"l2": "working set per iteration (>0.5 GB per GPU) exceeds the 126 MB L2; no flush needed",
+                    "e2e": "one forward() of `steps` iterations incl. H2D of this rank's sos maps, D2H of its wavefields, and (N > 1) one NCCL "
+                           "gather of wavefields + residual histories on rank 0 with D2H of the histories; bytes are per-step averages of rank 0"})
         line = {
             "metric": "Mpoint-iterations/s", "value": value, "unit": "Mpoint-iterations/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": f"{n}x{n} synthetic heterogeneous sos maps, batch {b_local} per GPU ({b_total} total), "
-                                   f"point source [30,{n // 2}], jcp_paper weights", "n": n, "batch_per_gpu": b_local,
-                       "global_batch": b_total, "parallelism": f"batch-sharded x{world}, no in-loop collective",
-                       "l2": "working set per iteration (>4 GB) exceeds the 126 MB L2; no flush needed",
-                       "e2e": "one forward() of `steps` iterations incl. H2D of sos and D2H of wavefield+rmse; bytes are per-step averages"},
+            "data": "synthetic", "config": cfg,
             "e2e": {"value": e2e_val, "unit": "Mpoint-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "kernels_per_iteration": int(lib.hn_kernels_per_iteration(ctx)),
+            "kernels_per_iteration": int(launches // K) if K else None,
             "clocks": clocks,
+            "sustained": sustained,
+            "weak_scaling": weak,
+            "other_configs": others,
             "roofline": roof[0],
             "roofline_kernels": roof[1:],
             "roofline_stage_unet": {"bound": "tensor", "achieved": ach_tf, "peak": tf32_peak, "unit": "TFLOP/s",
                                     "frac": ach_tf / tf32_peak if tf32_peak else None, "stage_ms": st_ms[0],
                                     "note": "16103.25 FLOP/point over the whole conv stack vs the dense TF32-rate peak "
-                                            f"({peaks['source']} bf16 burst / 2); the C_out=8 GEMMs are HBM-bound, see `roofline`",
+                                            f"({peaks['source']} bf16 burst / 2).  The C_out = 8 GEMMs (N <= 48, K = 16 MMAs) are bound by the "
+                                            "shared-memory operand fetch of tcgen05.mma, not by the tensor math or by HBM (DESIGN.md 4.2); "
+                                            "per-kernel HBM fractions are in `roofline` / `roofline_kernels`",
                                     "engine": solver._engine},
             "roofline_stage_spectral": {"bound": "hbm", "achieved": ach_gb, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                         "frac": ach_gb / peaks["hbm_gbs"], "stage_ms": st_ms[1],
                                         "algorithmic_bytes_per_point": BYTES_PER_POINT_SPECTRAL},
             "cpu_baseline": cpu,
+            "gpu_eager_baseline": gpu_eager,
             "ms_to_residual_1e-3": ttr,
             "readme_lens_ms_to_residual_1e-3": readme,
-            "final_rmse_max": float(rmse_buf[K - 1].max().item()),
+            "final_rmse_max": final_rmse_max,
         }
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -419,12 +604,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=256)
-    ap.add_argument("--batch", type=int, default=256, help="batch per GPU (weak) or total (strong)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--batch", type=int, default=256, help="total batch, sharded over the GPUs (strong) or batch per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--cpu-iters", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--residual-iters", type=int, default=1000, help="iteration cap of the time-to-residual-1e-3 run (0: skip)")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--gpu-baseline-batch", type=int, default=256)
+    ap.add_argument("--no-extras", action="store_true", help="skip the weak-scaling / other-configuration measurements")
+    ap.add_argument("--residual-iters", type=int, default=1000, help="iterations of the sustained / time-to-residual-1e-3 run (0: skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

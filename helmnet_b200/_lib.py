@@ -29,6 +29,7 @@ _SIGS = {
     "hn_destroy": (C.c_int, [_P]),
     "hn_load_weights": (C.c_int, [_P, _P, C.c_size_t]),
     "hn_set_source": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int64), _P]),
+    "hn_point_sources": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.c_double, C.c_double, C.c_int, _P, _P]),
     "hn_reset": (C.c_int, [_P, _P, C.c_int, _P]),
     "hn_set_state": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),
     "hn_run": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),

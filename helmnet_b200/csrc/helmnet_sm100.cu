@@ -54,6 +54,27 @@ static int fail(int code, const std::string& msg) {
         if (rc_ != HN_OK) return rc_; \
     } while (0)
 
+// Every ABI entry point runs with the context's device current and restores the caller's device on exit, so two
+// contexts on different GPUs can be driven from one host thread (and PyTorch's current device is left alone).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+#ifndef HN_EMU
+        if (device >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+#else
+        (void)device;
+#endif
+    }
+    ~DeviceGuard() {
+#ifndef HN_EMU
+        if (switched) cudaSetDevice(prev);
+#endif
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 struct ConvW {      // offsets (in floats) into the packed device blob
     size_t w = 0, b = 0, slope = 0;
     size_t b8 = 0;            // bias zero-padded to 8 entries (tcgen05 kernels always read 8)
@@ -140,6 +161,13 @@ struct hn_ctx {
 
 // amax slot ids
 enum : int { S_X = 0, S_MID = 5, S_SKIP = 10, S_UPO = 14, S_DEC = 18, S_BOT = 22, S_STATE = 23 /* + 2*d + buf */, S_IN6 = 31, S_DMID = 32, S_IMID = 36, S_WF = 37 /* +buf */, S_RES = 39 /* +buf */, S_COUNT = 41 };
+
+#ifndef HN_EMU
+static void drop_graphs(hn_ctx* c) {
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    c->graphs.clear();
+}
+#endif
 
 static int dalloc(hn_ctx* c, void** p, size_t bytes) {
     if (bytes == 0) bytes = 16;
@@ -645,10 +673,20 @@ static Conv3Args conv_args(hn_ctx* c, const ConvW& w, const float* inA, const fl
 static int set_smem_attrs(hn_ctx* c) {
     HN_CUDA(cudaFuncSetAttribute(down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DN_SMEM));
     HN_CUDA(cudaFuncSetAttribute(up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UP_SMEM));
-    HN_CUDA(cudaFuncSetAttribute(spectral_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)spectral_smem_bytes(c->n, c->rows_L, c->pml)));
-    HN_CUDA(cudaFuncSetAttribute(spectral_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)spectral_smem_bytes(c->n, c->cols_CW, c->pml)));
+    // the attribute is per function and device, not per context: keep the running maximum over all contexts, or a second
+    // context with a smaller domain would lower the limit under the first one's launches
+    static int rows_max[16] = {0}, cols_max[16] = {0};
+    int& rmax = rows_max[c->device & 15];
+    int& cmax = cols_max[c->device & 15];
+    const int rneed = (int)spectral_smem_bytes(c->n, c->rows_L, c->pml), cneed = (int)spectral_smem_bytes(c->n, c->cols_CW, c->pml);
+    if (rneed > rmax) {
+        HN_CUDA(cudaFuncSetAttribute(spectral_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rneed));
+        rmax = rneed;
+    }
+    if (cneed > cmax) {
+        HN_CUDA(cudaFuncSetAttribute(spectral_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cneed));
+        cmax = cneed;
+    }
     HN_CUDA(cudaFuncSetAttribute(s256::spectral_cols256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s256::COLS_SMEM_BYTES));
     HN_CUDA(cudaFuncSetAttribute(s512::spectral_rows512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s512::ROWS_SMEM_BYTES));
     HN_CUDA(cudaFuncSetAttribute(s512::spectral_cols512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s512::COLS_SMEM_BYTES));
@@ -1053,7 +1091,7 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     if (e != cudaSuccess || ndev == 0)
         return fail(HN_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return fail(HN_ERR_ARG, "bad device ordinal");
-    HN_CUDA(cudaSetDevice(device));
+    DeviceGuard dev_guard(device);
     cudaDeviceProp prop;
     HN_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(HN_ERR_CUDA, "libhelmnet_sm100 needs a compute capability 10.x (Blackwell) device");
@@ -1149,8 +1187,8 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
 
 int hn_destroy(hn_ctx* c) {
     if (!c) return HN_OK;
+    DeviceGuard dev_guard(c->device);
 #ifndef HN_EMU
-    cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
 #endif
@@ -1161,6 +1199,7 @@ int hn_destroy(hn_ctx* c) {
 }
 
 int hn_load_weights(hn_ctx* c, const float* host_blob, size_t n_floats) {
+    DeviceGuard dev_guard(c ? c->device : -1);
     if (!c || !host_blob) return fail(HN_ERR_ARG, "NULL argument");
     if (n_floats != HN_NUM_WEIGHTS) return fail(HN_ERR_ARG, "expected 48160 floats (HybridNet features=8 depth=4 state=2)");
     Packer pk;
@@ -1204,8 +1243,10 @@ int hn_load_weights(hn_ctx* c, const float* host_blob, size_t n_floats) {
     if (!cur.ok || cur.left != 0) return fail(HN_ERR_ARG, "weight blob does not match the HybridNet state_dict layout");
     if (pk.blob.size() > 65536) return fail(HN_ERR_STATE, "packed weights exceed the reserved buffer");
 #ifndef HN_EMU
-    HN_CUDA(cudaSetDevice(c->device));
     HN_CUDA(cudaDeviceSynchronize());
+    // The captured iteration graphs carry per-layer constants BY VALUE (biases, PReLU slopes, block scales, the 1x1 outc
+    // weights are kernel parameters read from c->whost at capture time): drop them so the next hn_run re-captures.
+    drop_graphs(c);
 #endif
     HN_CUDA(cudaMemcpy(c->wdev, pk.blob.data(), pk.blob.size() * 4, cudaMemcpyHostToDevice));
     c->whost = pk.blob;   // host copy: small per-layer constants are passed to the tcgen05 kernels as launch parameters
@@ -1216,6 +1257,7 @@ int hn_load_weights(hn_ctx* c, const float* host_blob, size_t n_floats) {
 }
 
 int hn_set_source(hn_ctx* c, const float* d_src, int src_batch, const int64_t strides[4], void* stream) {
+    DeviceGuard dev_guard(c ? c->device : -1);
     if (!c || !d_src || !strides) return fail(HN_ERR_ARG, "NULL argument");
     if (src_batch < 1 || src_batch > c->max_batch) return fail(HN_ERR_ARG, "source batch out of range");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1229,6 +1271,24 @@ int hn_set_source(hn_ctx* c, const float* d_src, int src_batch, const int64_t st
     return HN_OK;
 }
 
+int hn_point_sources(int device, int n, int count, const int32_t* d_locations, double amplitude, double arg, int smooth, float* d_out,
+                     void* stream) {
+    if (!d_locations || !d_out) return fail(HN_ERR_ARG, "NULL argument");
+    if (n <= 0 || count <= 0) return fail(HN_ERR_ARG, "domain size and source count must be positive");
+    if (smooth && n < 5) return fail(HN_ERR_ARG, "smoothed sources need a domain of at least 5 points");
+#ifndef HN_EMU
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(HN_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(HN_ERR_ARG, "bad device ordinal");
+#endif
+    DeviceGuard dev_guard(device);
+    const size_t total = (size_t)count * n * n;
+    HN_LAUNCH(point_sources_kernel, dim3(grid1d(total)), dim3(LAY_THREADS), 0, (cudaStream_t)stream, reinterpret_cast<const int*>(d_locations),
+              count, n, (float)amplitude, (float)cos(arg), (float)sin(arg), smooth, d_out);
+    HN_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
 static int check_ready(hn_ctx* c, int batch) {
     if (!c) return fail(HN_ERR_ARG, "ctx is NULL");
     if (batch < 1 || batch > c->max_batch) return fail(HN_ERR_ARG, "batch out of range for this context");
@@ -1239,6 +1299,7 @@ static int check_ready(hn_ctx* c, int batch) {
 }
 
 int hn_reset(hn_ctx* c, const float* d_sos, int batch, void* stream) {
+    DeviceGuard dev_guard(c ? c->device : -1);
     HN_TRY(check_ready(c, batch));
     if (!d_sos) return fail(HN_ERR_ARG, "d_sos is NULL");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1262,6 +1323,7 @@ int hn_reset(hn_ctx* c, const float* d_sos, int batch, void* stream) {
 
 int hn_set_state(hn_ctx* c, const float* d_wf, const float* d_res, const float* d_ksq, const float* d_hflat, int batch,
                  void* stream) {
+    DeviceGuard dev_guard(c ? c->device : -1);
     HN_TRY(check_ready(c, batch));
     if (!(d_wf && d_res && d_ksq) && (d_wf || d_res || d_ksq) && !(c->problem_set && c->batch == batch))
         return fail(HN_ERR_STATE, "partial field update needs an existing solve state of the same batch");
@@ -1317,6 +1379,7 @@ static int copy_states_out(hn_ctx* c, float* d_hflat, int batch, cudaStream_t st
 }
 
 int hn_get(hn_ctx* c, float* d_wf, float* d_res, float* d_hflat, void* stream) {
+    DeviceGuard dev_guard(c ? c->device : -1);
     if (!c) return fail(HN_ERR_ARG, "ctx is NULL");
     if (!c->problem_set) return fail(HN_ERR_STATE, "no solve state: call hn_reset or hn_set_state first");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1338,6 +1401,7 @@ int hn_get(hn_ctx* c, float* d_wf, float* d_res, float* d_hflat, void* stream) {
 }
 
 int hn_get_states(hn_ctx* c, float* d_hflat, int batch, void* stream) {
+    DeviceGuard dev_guard(c ? c->device : -1);
     if (!c || !d_hflat) return fail(HN_ERR_ARG, "NULL argument");
     if (batch < 1 || batch > c->max_batch) return fail(HN_ERR_ARG, "batch out of range for this context");
     HN_TRY(copy_states_out(c, d_hflat, batch, (cudaStream_t)stream));
@@ -1347,7 +1411,8 @@ int hn_get_states(hn_ctx* c, float* d_hflat, int batch, void* stream) {
 
 #ifndef HN_EMU
 static int get_graph(hn_ctx* c, int B, cudaGraphExec_t* out) {
-    const long long key = ((long long)B << 8) | ((long long)c->cur << 4) | (long long)c->engine;
+    // the source pointer offset / broadcast flag are baked into the spectral kernel's parameters: part of the key
+    const long long key = ((long long)B << 9) | ((long long)(c->src_batch > 1 ? 1 : 0) << 8) | ((long long)c->cur << 4) | (long long)c->engine;
     auto it = c->graphs.find(key);
     if (it != c->graphs.end()) {
         *out = it->second;
@@ -1383,6 +1448,7 @@ static int get_graph(hn_ctx* c, int B, cudaGraphExec_t* out) {
 #endif
 
 int hn_run(hn_ctx* c, int n_iters, float* d_rmse, float* d_wf_hist, float* d_res_hist, float* d_h_hist, void* stream) {
+    DeviceGuard dev_guard(c ? c->device : -1);
     if (!c) return fail(HN_ERR_ARG, "ctx is NULL");
     if (!c->problem_set) return fail(HN_ERR_STATE, "no solve state: call hn_reset or hn_set_state first");
     if (n_iters < 0) return fail(HN_ERR_ARG, "n_iters < 0");
@@ -1394,8 +1460,7 @@ int hn_run(hn_ctx* c, int n_iters, float* d_rmse, float* d_wf_hist, float* d_res
     if (need > c->ssq_cap) {
 #ifndef HN_EMU
         HN_CUDA(cudaStreamSynchronize(st));
-        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);   // graphs hold the old ssq pointer
-        c->graphs.clear();
+        drop_graphs(c);   // graphs hold the old ssq pointer
 #endif
         if (c->ssq) cudaFree(c->ssq);
         c->ssq = nullptr;
@@ -1443,6 +1508,7 @@ int hn_run(hn_ctx* c, int n_iters, float* d_rmse, float* d_wf_hist, float* d_res
 }
 
 int hn_residual(hn_ctx* c, const float* d_x, const float* d_ksq, float* d_out, float* d_rmse, int batch, void* stream) {
+    DeviceGuard dev_guard(c ? c->device : -1);
     HN_TRY(check_ready(c, batch));
     if (!d_x || !d_out) return fail(HN_ERR_ARG, "NULL argument");
     if (!d_ksq && !(c->problem_set && c->batch == batch)) return fail(HN_ERR_STATE, "no k_sq in the context for this batch");
@@ -1464,6 +1530,7 @@ int hn_residual(hn_ctx* c, const float* d_x, const float* d_ksq, float* d_out, f
 }
 
 int hn_laplacian(hn_ctx* c, const float* d_x, float* d_out, int batch, void* stream) {
+    DeviceGuard dev_guard(c ? c->device : -1);
     if (!c || !d_x || !d_out) return fail(HN_ERR_ARG, "NULL argument");
     if (batch < 1 || batch > c->max_batch) return fail(HN_ERR_ARG, "batch out of range for this context");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1479,6 +1546,7 @@ int hn_laplacian(hn_ctx* c, const float* d_x, float* d_out, int batch, void* str
 }
 
 int hn_unet(hn_ctx* c, const float* d_in, float* d_out, int batch, void* stream) {
+    DeviceGuard dev_guard(c ? c->device : -1);
     if (!c || !d_in || !d_out) return fail(HN_ERR_ARG, "NULL argument");
     if (batch < 1 || batch > c->max_batch) return fail(HN_ERR_ARG, "batch out of range for this context");
     if (!c->weights_set) return fail(HN_ERR_STATE, "hn_load_weights has not been called");
@@ -1502,6 +1570,7 @@ int64_t hn_launch_count(const hn_ctx* c) { return c ? c->launches : 0; }
 int hn_kernels_per_iteration(const hn_ctx* c) { return c ? c->kernels_per_iter : HN_ERR_ARG; }
 
 int hn_debug_tensor(hn_ctx* c, const char* name, float* d_out, int batch, void* stream) {
+    DeviceGuard dev_guard(c ? c->device : -1);
     if (!c || !name || !d_out) return fail(HN_ERR_ARG, "NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
     const std::string s(name);
@@ -1535,6 +1604,7 @@ int hn_set_engine(hn_ctx* c, int engine) {
 }
 
 int hn_sync_check(hn_ctx* c, void* stream) {
+    DeviceGuard dev_guard(c ? c->device : -1);
     if (!c) return fail(HN_ERR_ARG, "ctx is NULL");
 #ifndef HN_EMU
     HN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -1549,6 +1619,7 @@ int hn_sync_check(hn_ctx* c, void* stream) {
 // context's current buffers:  which = 0: inc conv #2 (8->8, level 0)   1: decode[0] conv #1 (16->8, level 0)
 //   2: enc[0].down   3: up[0]   4: spectral rows   5: spectral cols.   Used by bench.py for the per-kernel roofline.
 int hn_profile_layer(hn_ctx* c, int which, int reps, float* out_ms, void* stream) {
+    DeviceGuard dev_guard(c ? c->device : -1);
     if (!c || !out_ms || reps < 1) return fail(HN_ERR_ARG, "bad argument");
     if (!c->problem_set) return fail(HN_ERR_STATE, "no solve state");
     *out_ms = 0.f;
@@ -1662,6 +1733,7 @@ int hn_profile_layer(hn_ctx* c, int which, int reps, float* out_ms, void* stream
 }
 
 int hn_profile_iteration(hn_ctx* c, float out_ms[2], void* stream) {
+    DeviceGuard dev_guard(c ? c->device : -1);
     if (!c || !out_ms) return fail(HN_ERR_ARG, "NULL argument");
     if (!c->problem_set) return fail(HN_ERR_STATE, "no solve state");
     out_ms[0] = out_ms[1] = 0.f;

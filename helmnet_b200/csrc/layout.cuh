@@ -54,6 +54,36 @@ __global__ void src_strided_to_c2_kernel(const float* __restrict__ in, float2* _
         out[i] = make_float2(in[o], in[o + sc]);
     }
 }
+// Monochromatic point sources, one map per location (SourceModule.make_abs_spatial_map + spatial_map, source_module.py:41-116;
+// IterativeSolver.set_multiple_sources, hybridnet.py:161-170), written as the NCHW tensor [S,2,n,n] the reference builds.
+// The reference forms |ifft2(ifftshift(fftshift(fft2(delta)) * W))| with W = 1 or the outer product of two (periodic)
+// Blackman windows.  The shifted window is 0.42 + 0.5 cos(2 pi k/n) + 0.08 cos(4 pi k/n) over the frequency index k, whose
+// inverse DFT is the 5-tap kernel g = [0.04, 0.25, 0.42, 0.25, 0.04], so the map is amplitude * g(y - r) * g(x - c) with
+// periodic wrap (a delta without smoothing) -- no transform needed.  real = |map| cos(arg), imag = |map| sin(arg).
+__global__ void point_sources_kernel(const int* __restrict__ loc, int count, int n, float amplitude, float cos_arg, float sin_arg,
+                                     int smooth, float* __restrict__ out) {
+    const size_t hw = (size_t)n * n, total = (size_t)count * hw;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t s = i / hw, p = i - s * hw;
+        const int y = (int)(p / n), x = (int)(p % n);
+        int dy = y - loc[2 * s], dx = x - loc[2 * s + 1];
+        dy = ((dy % n) + n) % n;
+        dx = ((dx % n) + n) % n;
+        if (dy > n / 2) dy = n - dy;
+        if (dx > n / 2) dx = n - dx;
+        float gy, gx;
+        if (smooth) {
+            gy = dy == 0 ? 0.42f : dy == 1 ? 0.25f : dy == 2 ? 0.04f : 0.f;
+            gx = dx == 0 ? 0.42f : dx == 1 ? 0.25f : dx == 2 ? 0.04f : 0.f;
+        } else {
+            gy = dy == 0 ? 1.f : 0.f;
+            gx = dx == 0 ? 1.f : 0.f;
+        }
+        const float v = fabsf(amplitude) * gy * gx;
+        out[(s * 2) * hw + p] = v * cos_arg;
+        out[(s * 2 + 1) * hw + p] = v * sin_arg;
+    }
+}
 // get_initials + initial residual: k_sq = (omega/sos)^2, wf = 0, res = L(0) + k_sq*0 - source = -source
 __global__ void reset_kernel(const float* __restrict__ sos, float* __restrict__ ksq, float2* __restrict__ wf,
                              float2* __restrict__ res, const float2* __restrict__ src, int src_batch, float omega, int hw,

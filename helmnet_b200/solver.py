@@ -308,12 +308,36 @@ class IterativeSolver(nn.Module):
                 self.set_source()
 
     def set_multiple_sources(self, source_locations):
-        maps = []
+        """hybridnet.py:161-170: one point-source map per location.  One CUDA kernel writes all S maps (hn_point_sources: the
+        delta / Blackman-smoothed map of SourceModule in closed form) instead of S passes through torch.fft; the source module
+        is left at the last location, as in the reference."""
+        locs = [[int(l[0]), int(l[1])] for l in source_locations]
+        if not locs:
+            raise ValueError("set_multiple_sources needs at least one location")
+        n = self.hparams.domain_size
+        for r, c in locs:
+            if not (0 <= r < n and 0 <= c < n):
+                raise IndexError(f"source location [{r}, {c}] is outside the {n} x {n} domain")
+        dev, lib = self.device, self.lib
+        if lib.requires_cuda and dev.type != "cuda":
+            # host-side construction (solver still on the CPU, e.g. before .to('cuda')): plain PyTorch setup as the reference does
+            maps = []
+            with torch.no_grad():
+                for loc in locs:
+                    self.source_module.set_new_location(loc)
+                    maps.append(self.source_module.spatial_map(0).permute(0, 3, 1, 2))
+                self.set_source_maps(torch.cat(maps, 0))
+            return
+        hp = self.hparams
+        loc_t = torch.tensor(locs, dtype=torch.int32, device=dev)
+        out = torch.empty(len(locs), 2, n, n, device=dev)
+        idx = dev.index if dev.index is not None else (torch.cuda.current_device() if dev.type == "cuda" else 0)
+        lib.check(lib.hn_point_sources(idx, n, len(locs), self._ptr(loc_t), float(hp.source_amplitude), float(hp.source_phase),
+                                       1 if hp.source_smoothing else 0, self._ptr(out), self._stream()), "hn_point_sources")
         with torch.no_grad():
-            for loc in source_locations:
-                self.source_module.set_new_location(loc)
-                maps.append(self.source_module.spatial_map(0).permute(0, 3, 1, 2))
-            self.set_source_maps(torch.cat(maps, 0))
+            self.source_module.set_new_location(locs[-1])
+        self._loc_keepalive = loc_t
+        self.set_source_maps(out)
 
     # ---- CUDA context management -----------------------------------------------------------------------
     @property
@@ -347,15 +371,19 @@ class IterativeSolver(nn.Module):
         self.lib.check_tensor(t, name)
         return t.float().contiguous()
 
-    def _ensure_ctx(self, batch: int):
+    def _ensure_ctx(self, batch: int, need_weights: bool = True, need_source: bool = True):
         lib, dev = self.lib, self.device
         if lib.requires_cuda and dev.type != "cuda":
             raise _lib.HelmnetError("IterativeSolver is on the CPU: call solver.to('cuda:0'); there is no CPU path")
         hp = self.hparams
         key = (str(dev), int(hp.domain_size), int(hp.PMLsize), float(hp.sigma_max), float(hp.k), float(hp.omega))
-        if self._ctx is None or key != self._ctx_key or batch > self._ctx_max_batch:
+        # the context must hold the current source maps as well ([S,2,N,N], S may exceed this call's batch: the reference
+        # broadcasts a [1,...] field against an [S,...] source)
+        src_b = int(self.source.shape[0]) if getattr(self, "source", None) is not None and self.source.dim() == 4 else 1
+        want = max(batch, src_b, 1)
+        if self._ctx is None or key != self._ctx_key or want > self._ctx_max_batch:
             self._release_ctx()
-            max_batch = max(batch, 1)
+            max_batch = want
             ctx = C.c_void_p()
             idx = dev.index if dev.index is not None else (torch.cuda.current_device() if dev.type == "cuda" else 0)
             lib.check(lib.hn_create(C.byref(ctx), idx, hp.domain_size, max_batch, hp.PMLsize, float(hp.sigma_max),
@@ -364,11 +392,11 @@ class IterativeSolver(nn.Module):
             self._weights_dirty = self._source_dirty = True
             if lib.requires_cuda:
                 lib.check(lib.hn_set_engine(ctx, self._engine), "hn_set_engine")
-        if self._weights_dirty:
+        if self._weights_dirty and need_weights:
             blob = self.f.weight_blob()
             lib.check(lib.hn_load_weights(self._ctx, self._ptr(blob), blob.numel()), "hn_load_weights")
             self._weights_dirty = False
-        if self._source_dirty:
+        if self._source_dirty and need_source:
             src = self.source.detach()
             if src.device != dev:
                 src = src.to(dev)
@@ -412,7 +440,7 @@ class IterativeSolver(nn.Module):
 
     def apply_laplacian(self, x: torch.Tensor):
         x = self._prep(x, "x")
-        ctx = self._ensure_ctx(x.shape[0])
+        ctx = self._ensure_ctx(x.shape[0], need_weights=False, need_source=False)   # L(u) needs neither
         out = torch.empty_like(x)
         self.lib.check(self.lib.hn_laplacian(ctx, self._ptr(x), self._ptr(out), x.shape[0], self._stream()), "hn_laplacian")
         return out
@@ -420,6 +448,13 @@ class IterativeSolver(nn.Module):
     def get_residual(self, x: torch.Tensor, k_sq: torch.Tensor):
         x = self._prep(x, "x")
         k_sq = self._prep(k_sq, "k_sq")
+        s_b = int(self.source.shape[0])
+        if x.shape[0] == 1 and s_b > 1:      # hybridnet.py:556 broadcasts a single field against S source maps
+            x = x.expand(s_b, -1, -1, -1).contiguous()
+        if k_sq.shape[0] == 1 and x.shape[0] > 1:
+            k_sq = k_sq.expand(x.shape[0], -1, -1, -1).contiguous()
+        if s_b not in (1, x.shape[0]):
+            raise ValueError(f"source holds {s_b} maps but the field batch is {x.shape[0]}: they must match (or one of them be 1)")
         ctx = self._ensure_ctx(x.shape[0])
         out = torch.empty_like(x)
         self.lib.check(self.lib.hn_residual(ctx, self._ptr(x), self._ptr(k_sq), self._ptr(out), self._ptr(None), x.shape[0],

@@ -66,6 +66,14 @@ int hn_load_weights(hn_ctx* ctx, const float* host_blob, size_t n_floats);
  * (strides 2N^2, 1, 2N, 2) is accepted as is.  src_batch is 1 (broadcast) or the batch size. */
 int hn_set_source(hn_ctx* ctx, const float* d_src, int src_batch, const int64_t strides[4], void* stream);
 
+/* IterativeSolver.set_multiple_sources / SourceModule.make_abs_spatial_map + spatial_map
+ * (helmnet/hybridnet.py:161-170, helmnet/source_module.py:41-116): one monochromatic point source map per location,
+ * d_out [count, 2, N, N] (NCHW, contiguous; channel 0 = |map| cos(arg), channel 1 = |map| sin(arg), arg = omega*t + phase).
+ * d_locations is int32 [count, 2] = (row, col) on `device`.  smooth != 0 applies the reference's Blackman window in the spatial
+ * frequency domain (in closed form: a separable 5-tap kernel around the location, periodic wrap).  Needs no context. */
+int hn_point_sources(int device, int n, int count, const int32_t* d_locations, double amplitude, double arg, int smooth,
+                     float* d_out, void* stream);
+
 /* IterativeSolver.get_initials + HybridNet.clear_states + the initial get_residual
  * (helmnet/hybridnet.py:522-538, 670-673; helmnet/architectures.py:415-417):
  * k_sq = (omega/sos)^2, wavefield = 0, hidden states = 0, residual = L(0) + k_sq*0 - source.

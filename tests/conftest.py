@@ -23,6 +23,18 @@ def rel_l2(a, b):
     return float((a - b).norm() / b.norm())
 
 
+def record(name, **vals):
+    """Append measured parity numbers to gpurun_out/parity_measured.jsonl (copied into profiles/ per round)."""
+    import json
+    d = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_measured.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **{k: (float(v) if not isinstance(v, (list, str, int)) else v) for k, v in vals.items()}}) + "\n")
+    except OSError:
+        pass
+
+
 @pytest.fixture(scope="session")
 def gold():
     def load(name):

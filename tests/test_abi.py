@@ -38,6 +38,31 @@ def test_sass_is_sm100_and_uses_ffma2():
     assert out.count("FFMA2") > 1000
 
 
+def test_sass_census_of_the_tensor_core_path():
+    """The default engine is tcgen05/TMEM/TMA code, not a recompiled mma.sync path: UTCHMMA (tcgen05.mma kind::f16),
+    LDTM/STTM (tcgen05.ld/st), UBLKCP (cp.async.bulk), ACQBULK (griddepcontrol.wait) per kernel family."""
+    import subprocess
+    from helmnet_b200 import build
+    out = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True).stdout
+    census, name = {}, None
+    for line in out.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+            census[name] = {"UTCHMMA": 0, "LDTM": 0, "STTM": 0, "UBLKCP": 0, "ACQBULK": 0, "UTCBAR": 0}
+        elif name:
+            for k_ in census[name]:
+                if k_ in line:
+                    census[name][k_] += 1
+    fam = lambda key: [v for k_, v in census.items() if key in k_]
+    for key in ("dconv_tcf_kernel", "down_tcr_kernel", "up_tcr_kernel", "conv3x3_tcr_kernel"):
+        ks = fam(key)
+        assert ks, key
+        for v in ks:
+            assert v["UTCHMMA"] > 0 and v["LDTM"] > 0 and v["UBLKCP"] > 0 and v["ACQBULK"] > 0, (key, v)
+    assert sum(v["UTCHMMA"] for v in census.values()) > 500
+    assert not any("HMMA." in l and "UTCHMMA" not in l for l in out.splitlines()), "legacy mma.sync found"
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_cpu_fallback():
     from helmnet_b200 import IterativeSolver

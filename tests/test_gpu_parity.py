@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import rel_l2
+from conftest import record, rel_l2
 
 pytestmark = pytest.mark.gpu
 PER_ITER_TOL = 1e-5
@@ -124,16 +124,66 @@ def test_trajectory_readme_golden(cuda_solver, gold):
 
 
 def test_trajectory_bench_workload_golden(cuda_solver, gold):
-    """The bench.py workload (synthetic heterogeneous 256^2 maps) against the unmodified reference: one iteration from the
-    common start at the per-iteration bar; after 12 iterations well inside the final-wavefield bar (1e-3)."""
+    """The bench.py workload (config_sos("C3"): 8(d) outline maps + smooth heterogeneity, 256^2) against the unmodified
+    reference.  Iteration 0 (common start) at the per-iteration bar.  Later iterations use the reference's float64 run as the
+    arbiter: the reference's own fp32 trajectory drifts from it (2.4e-5 at iteration 11 on these maps), so the CUDA path must
+    stay within 2x the reference-fp32 distance to the fp64 trajectory (wavefields and RMSE history alike)."""
     g = gold("traj_bench_n256_b2.npz")
     s = cuda_solver
     s.set_domain_size(256, source_location=[30, 128])
     out = s.forward(torch.tensor(g["sos"]).cuda(), num_iterations=12, return_wavefields=True)
     e0 = rel_l2(out["wavefields"][0], g["wavefields"][0])
-    e11 = rel_l2(out["wavefields"][11], g["wavefields"][1])
-    assert e0 < PER_ITER_TOL and e11 < 1e-4, (e0, e11)
-    assert rel_l2(out["residual_rmse"], g["rmse"]) < 1e-4
+    assert e0 < PER_ITER_TOL, e0
+    meas = {"engine": s._engine, "it0_vs_ref32": e0}
+    for i, k in enumerate(g["keep"]):
+        ours64 = rel_l2(out["wavefields"][int(k)], g["wavefields64"][i])
+        ref64 = rel_l2(g["wavefields"][i], g["wavefields64"][i])
+        meas[f"it{int(k)}_ours_vs_fp64"], meas[f"it{int(k)}_ref32_vs_fp64"] = ours64, ref64
+        assert ours64 <= 2.0 * ref64 + 1e-6, (int(k), ours64, ref64)
+    rm_ours, rm_ref = rel_l2(out["residual_rmse"], g["rmse64"]), rel_l2(g["rmse"], g["rmse64"])
+    meas["rmse_ours_vs_fp64"], meas["rmse_ref32_vs_fp64"] = rm_ours, rm_ref
+    meas["it11_vs_ref32"] = rel_l2(out["wavefields"][11], g["wavefields"][1])
+    record("bench_workload_fp64_arbiter", **meas)
+    print(meas)
+    assert rm_ours <= 2.0 * rm_ref + 1e-6, (rm_ours, rm_ref)
+    assert meas["it11_vs_ref32"] < FINAL_TOL
+
+
+def test_readme_full_iteration_count(cuda_solver, gold):
+    """config[0] at its full K = 1000 (support_functions.py:454-459): final wavefield <= 1e-3 of the reference's, the RMSE
+    history within the same bound, first RMSE < 1e-3 at iteration 52, SURVEY.md 8c landmarks ||wf||_2 = 55.10, max |wf| = 2.547."""
+    g = gold("traj_readme_n256_k1000.npz")
+    s = cuda_solver
+    sos = np.ones((256, 256)); sos[100:170, 30:240] = np.tile(np.linspace(2, 1, 210), (70, 1))
+    s.set_domain_size(256, source_location=[30, 128])
+    out = s.forward(torch.tensor(sos).float()[None, None].cuda(), num_iterations=1000, return_residuals=False)
+    wf = out["wavefields"][0]
+    rm = out["residual_rmse"].cpu().numpy()[:, 0]
+    e_wf, e_wf64 = rel_l2(wf, g["wavefield"]), rel_l2(wf, g["wavefield64"])
+    e_rm = float(np.max(np.abs(rm - g["rmse"]) / g["rmse"]))
+    record("readme_k1000", engine=s._engine, final_vs_ref32=e_wf, final_vs_fp64=e_wf64, ref32_vs_fp64=rel_l2(g["wavefield"], g["wavefield64"]),
+           rmse_max_rel=e_rm, wf_l2=float(wf.double().norm()), wf_max=float(wf.abs().max()), rmse_last=float(rm[-1]))
+    assert e_wf < FINAL_TOL and e_rm < FINAL_TOL * 10, (e_wf, e_rm)       # the plateau RMSE (1.8e-5) is a difference of O(1) terms
+    assert float(np.max(np.abs(rm[:200] - g["rmse"][:200]) / g["rmse"][:200])) < FINAL_TOL
+    assert int(np.argmax(rm < 1e-3)) == 52
+    assert abs(float(wf.double().norm()) - 55.10) < 0.01 and abs(float(wf.abs().max()) - 2.547) < 1e-3
+
+
+def test_c4_full_iteration_count(cuda_solver, gold):
+    """A C4-style map (512^2, high-contrast outline, source [450,256]) at the configuration's K = 3000 (support_functions.py:328-333)."""
+    if cuda_solver._engine == 0:
+        pytest.skip("3000 iterations at 512^2 on the fp32 CUDA-core engine take minutes; engines 1 and 2 cover the path")
+    g = gold("traj_c4_n512_k3000.npz")
+    s = cuda_solver
+    s.set_domain_size(512, source_location=[450, 256])
+    out = s.forward(torch.tensor(g["sos"]).cuda(), num_iterations=3000, return_residuals=False)
+    wf = out["wavefields"][0]
+    rm = out["residual_rmse"].cpu().numpy()[:, 0]
+    e_wf = rel_l2(wf, g["wavefield"])
+    e_rm = rel_l2(rm, g["rmse"])
+    record("c4_k3000", engine=s._engine, final_vs_ref32=e_wf, final_vs_fp64=rel_l2(wf, g["wavefield64"]),
+           ref32_vs_fp64=rel_l2(g["wavefield"], g["wavefield64"]), rmse_traj_rel_l2=e_rm, rmse_last=float(rm[-1]), ref_rmse_last=float(g["rmse"][-1]))
+    assert e_wf < FINAL_TOL and e_rm < FINAL_TOL, (e_wf, e_rm)
 
 
 def test_trajectory_source_maps_golden(cuda_solver, gold):
@@ -218,6 +268,152 @@ def test_n_steps_and_variable_source(cuda_solver, gold):
     b = s.n_steps(o["wavefields"][0], k_sq, res, 2)
     assert rel_l2(a["wavefields"][0], b["wavefields"][0]) < 1e-6
     assert a["residual_rmse"].shape == (4, 3)
+
+
+def test_variable_source_golden(cuda_solver, gold):
+    """forward_variable_src against the unmodified reference (hybridnet.py:699-754): sources swapped at iterations 0 and 3."""
+    g, s0 = gold("variable_src_n64.npz"), gold("traj_srcmap_n64.npz")
+    s = cuda_solver
+    s.set_domain_size(64, source_map=torch.tensor(s0["source"]).cuda())
+    pairs = {"iteration": [int(i) for i in g["iterations"]], "src_maps": [torch.tensor(m).cuda() for m in g["src_maps"]]}
+    out = s.forward_variable_src(torch.tensor(s0["sos"]).cuda(), pairs, num_iterations=8, return_wavefields=True, return_states=True)
+    errs = [rel_l2(out["wavefields"][k], g["wavefields"][k]) for k in range(8)]
+    record("variable_src", engine=s._engine, max_wavefield_err=max(errs), rmse_err=rel_l2(out["residual_rmse"], g["rmse"]))
+    assert max(errs) < PER_ITER_TOL, errs
+    assert rel_l2(out["residual_rmse"], g["rmse"]) < PER_ITER_TOL
+    assert rel_l2(out["states"][-1], g["states_last"]) < 1e-4
+    assert rel_l2(out["residuals"][-1], g["residual_last"]) < 1e-3 and out["last_iteration"] == 7
+
+
+@pytest.mark.parametrize("smooth", [False, True])
+def test_multiple_sources_golden(cuda_solver, gold, smooth):
+    """set_multiple_sources with 3 locations (one per sample), plain and Blackman-smoothed (hybridnet.py:161-170,
+    source_module.py:41-79): the maps written by hn_point_sources and 6 iterations against the unmodified reference."""
+    g = gold("multi_source_n96.npz")
+    tag = "smooth" if smooth else "plain"
+    s = cuda_solver
+    old = s.hparams.source_smoothing
+    s.hparams.source_smoothing = smooth
+    try:
+        s.set_domain_size(96, source_location=[82, 48])
+        s.set_multiple_sources(g["locations"].tolist())
+        assert tuple(s.source.shape) == (3, 2, 96, 96) and s.source_module.get_location() == g["locations"][-1].tolist()
+        e_src = rel_l2(s.source, g[f"source_{tag}"])
+        out = s.forward(torch.tensor(g["sos"]).cuda(), num_iterations=6)
+        e_wf, e_rm = rel_l2(out["wavefields"][0], g[f"wavefield_{tag}"]), rel_l2(out["residual_rmse"], g[f"rmse_{tag}"])
+        record("multi_source_" + tag, engine=s._engine, source_err=e_src, wavefield_err=e_wf, rmse_err=e_rm)
+        assert e_src < 1e-6 and e_wf < PER_ITER_TOL and e_rm < PER_ITER_TOL, (e_src, e_wf, e_rm)
+    finally:
+        s.hparams.source_smoothing = old
+
+
+def test_test_step_and_result_files(cuda_solver, gold, tmp_path):
+    """The evaluation hooks (hybridnet.py:299-330; evaluate.py:27-29) write the two arrays the reference writes."""
+    g = gold("test_step_n96.npz")
+    s = cuda_solver
+    old = s.hparams.max_iterations, list(s.hparams.source_location)
+    s.hparams.max_iterations, s.hparams.source_location = int(g["max_iterations"]), [82, 48]
+    try:
+        s.set_domain_size(96, source_location=[82, 48])
+        sos = torch.tensor(g["sos"]).cuda()
+        outs = [s.test_step(sos[:2], 0), s.test_step(sos[2:], 1)]
+        s.test_epoch_end(outs, out_dir=str(tmp_path))
+        losses = np.load(tmp_path / "evolution_of_model_RMSE_on_test_set.npy")
+        wfs = np.load(tmp_path / "evolution_of_wavefields_on_test_set.npy")
+        assert losses.shape == g["losses"].shape and wfs.shape == g["wavefields"].shape
+        e_l, e_w = rel_l2(losses, g["losses"]), rel_l2(wfs, g["wavefields"])
+        record("test_step_files", engine=s._engine, losses_err=e_l, wavefields_err=e_w)
+        assert e_l < PER_ITER_TOL and e_w < PER_ITER_TOL, (e_l, e_w)
+    finally:
+        s.hparams.max_iterations, s.hparams.source_location = old
+
+
+def test_weight_reload_on_live_context(cuda_solver, f_weights):
+    """Cached iteration graphs carry per-layer constants by value: a weight reload on a live context must drop them."""
+    from oracle import helmnet_oracle as O
+    s, n = cuda_solver, 64
+    s.set_domain_size(n, source_location=[20, 30])
+    sos = (1.0 + 0.5 * torch.rand(2, 1, n, n, generator=torch.Generator().manual_seed(3)))
+    first = s.forward(sos.cuda(), num_iterations=4)["wavefields"][0].clone()
+    orig = {k_: v.clone() for k_, v in s.f.state_dict().items()}
+    g = torch.Generator().manual_seed(4)
+    changed = {k_: (v * (1.0 + 0.2 * torch.randn(v.shape, generator=g).to(v.device)) if v.dtype.is_floating_point else v) for k_, v in orig.items()}
+    try:
+        s.f.load_state_dict(changed)                      # evaluate.py:62 path -> hn_load_weights on the live context
+        got = s.forward(sos.cuda(), num_iterations=4)["wavefields"][0].clone()
+        orc = O.Oracle({k_: v.cpu() for k_, v in changed.items()}, n)
+        orc.set_source(O.point_source(n, [20, 30]))
+        ref = orc.forward(sos, 4)["wavefield"]
+        assert rel_l2(got, ref) < PER_ITER_TOL, rel_l2(got, ref)
+        assert rel_l2(got, first) > 1e-3                   # the new weights really changed the result
+    finally:
+        s.f.load_state_dict(orig)
+    again = s.forward(sos.cuda(), num_iterations=4)["wavefields"][0]
+    assert torch.equal(again, first)
+
+
+def test_source_switch_on_live_context(cuda_solver, f_weights):
+    """One broadcast source -> per-sample sources -> one broadcast source at the same batch on a live context (the source
+    batch is a parameter of the captured residual kernel)."""
+    from oracle import helmnet_oracle as O
+    s, n, b = cuda_solver, 64, 3
+    locs = [[10, 12], [40, 50], [30, 8]]
+    sos = (1.0 + 0.5 * torch.rand(b, 1, n, n, generator=torch.Generator().manual_seed(8)))
+    orc = O.Oracle(f_weights, n)
+
+    def check(src):
+        orc.set_source(src)
+        ref = orc.forward(sos, 5)
+        out = s.forward(sos.cuda(), num_iterations=5)
+        assert rel_l2(out["wavefields"][0], ref["wavefield"]) < PER_ITER_TOL
+        assert rel_l2(out["residual_rmse"], ref["rmse"]) < PER_ITER_TOL
+
+    s.set_domain_size(n, source_location=locs[0])
+    check(O.point_source(n, locs[0]))
+    s.set_multiple_sources(locs)
+    check(O.point_sources(n, locs))
+    s.set_multiple_sources([locs[1]])
+    check(O.point_source(n, locs[1]))
+    # a single field against S source maps broadcasts in get_residual (hybridnet.py:556)
+    s.set_multiple_sources(locs)
+    u = torch.randn(1, 2, n, n, generator=torch.Generator().manual_seed(9))
+    k_sq = torch.ones(1, 1, n, n)
+    ref = O.get_residual(u, k_sq, O.point_sources(n, locs), orc.op)
+    assert rel_l2(s.get_residual(u.cuda(), k_sq.cuda()), ref) < 1e-6
+
+
+def test_two_contexts_of_different_size(_cuda_solver_base):
+    """The dynamic shared-memory limit of the generic spectral kernels is per function, not per context: a second, smaller
+    domain must not lower it under the first context's launches."""
+    from helmnet_b200 import IterativeSolver
+    from conftest import CKPT
+    from oracle import helmnet_oracle as O
+    big = _cuda_solver_base
+    big.set_domain_size(480, source_location=[40, 40])
+    u = torch.randn(1, 480, 480, 2, generator=torch.Generator().manual_seed(1))
+    a = big.Lap(u.cuda()).clone()
+    small = IterativeSolver.load_from_checkpoint(CKPT, strict=False, test_data_path=None)
+    small.freeze(); small.to("cuda:0")
+    small.set_domain_size(96, source_location=[40, 40])
+    small.Lap(torch.randn(1, 96, 96, 2).cuda())
+    b = big.Lap(u.cuda())
+    big.sync_check()
+    assert torch.equal(a, b)
+    assert rel_l2(a, O.laplacian(u, O.make_operator(480, 8, 2.0, 1.0))) < 1e-6
+    assert torch.cuda.current_device() == 0
+
+
+def test_default_engine_is_the_fused_tcgen05_one(_cuda_solver_base, monkeypatch):
+    monkeypatch.delenv("HELMNET_ENGINE", raising=False)
+    from helmnet_b200 import IterativeSolver
+    from conftest import CKPT
+    s = IterativeSolver.load_from_checkpoint(CKPT, strict=False, test_data_path=None)
+    assert s._engine == 2
+    s.freeze(); s.to("cuda:0")
+    s.set_domain_size(64, source_location=[5, 5])
+    s.forward(torch.ones(1, 1, 64, 64).cuda(), num_iterations=1)
+    assert s.lib.hn_set_engine(s._ctx, 2) == 2
+    assert s.lib.hn_kernels_per_iteration(s._ctx) <= 30
 
 
 def test_large_amplitude_inputs_stay_in_range(cuda_solver, f_weights):
