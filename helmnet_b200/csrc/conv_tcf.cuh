@@ -53,15 +53,31 @@ __host__ __device__ constexpr size_t stage_row_bytes(int src, int nh) {
 }
 // ring depths in row PAIRS
 // (staging: the narrow variants have shared memory to spare and one strip per CTA, so their step time is the HBM latency divided
-//  by the number of row pairs in flight: eight pairs instead of two to four)
+//  by the number of row pairs in flight: six pairs (four for the 16-channel source) instead of two to four)
 #ifndef HN_TCF_NSP_NARROW
-#define HN_TCF_NSP_NARROW 8
+#define HN_TCF_NSP_NARROW 6
+#endif
+// operand-ring depths of the narrow (64- / 32-pixel) variants: one strip per CTA, so a step is bounded by the loops
+// converter(j + SRP1) -> MMA-1(j) and epilogue-1(p + SRP2) -> MMA-2(p); 0 = the depths of the wide variants
+// (measured, r2: four operand pairs per ring and a six / four deep staging ring instead of 2 / 2 / 8: 64^2 x 32 0.241 -> 0.228 ms
+//  per iteration, 64^2 x 256 0.563 -> 0.555, nothing lost elsewhere; the shared memory still allows two CTAs per SM)
+#ifndef HN_TCF_SRP1_NARROW
+#define HN_TCF_SRP1_NARROW 4
+#endif
+#ifndef HN_TCF_SRP2_NARROW
+#define HN_TCF_SRP2_NARROW 4
+#endif
+#ifndef HN_TCF_NSP_NARROW_B8
+#define HN_TCF_NSP_NARROW_B8 4
 #endif
 __host__ __device__ constexpr int nsp(int src, int nh) {
-    return (nh <= 0 && HN_TCF_NSP_NARROW > 0) ? HN_TCF_NSP_NARROW : (src == SRC_A8_B8 ? 2 : (src == SRC_INC ? 4 : 3));
+    return (nh <= 0 && HN_TCF_NSP_NARROW > 0) ? (src == SRC_A8_B8 ? HN_TCF_NSP_NARROW_B8 : HN_TCF_NSP_NARROW)
+                                              : (src == SRC_A8_B8 ? 2 : (src == SRC_INC ? 4 : 3));
 }
-__host__ __device__ constexpr int srp1(int src, int nh) { return groups_of(src) == 1 ? 4 : (nh == 2 ? 3 : 2); }
-__host__ __device__ constexpr int srp2(int src, int nh) { return 2; }
+__host__ __device__ constexpr int srp1(int src, int nh) {
+    return (nh <= 0 && HN_TCF_SRP1_NARROW > 0) ? HN_TCF_SRP1_NARROW : (groups_of(src) == 1 ? 4 : (nh == 2 ? 3 : 2));
+}
+__host__ __device__ constexpr int srp2(int src, int nh) { return (nh <= 0 && HN_TCF_SRP2_NARROW > 0) ? HN_TCF_SRP2_NARROW : 2; }
 __host__ __device__ constexpr size_t a1_row_bytes(int src, int nh) { return (size_t)groups_of(src) * 2 * psw(nh) * 16; }
 __host__ __device__ constexpr size_t a2_row_bytes(int nh) { return (size_t)2 * psw(nh) * 16; }
 __host__ __device__ constexpr size_t smem_bytes(int src, int nh) {

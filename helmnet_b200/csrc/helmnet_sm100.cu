@@ -97,6 +97,8 @@ struct hn_ctx {
     int engine = 2;            // 2: tcgen05 kernels with fused DoubleConvs (default), 1: tcgen05 one kernel per conv, 0: fp32 CUDA cores
     // resident fields
     float *wf = nullptr, *res = nullptr, *ksq = nullptr, *src = nullptr, *rx = nullptr;
+    unsigned char* src_nz = nullptr;   // [max_batch][n]: column j of source map s holds a non-zero (spectral.cuh: tile_source)
+    bool src_skip = true;              // HELMNET_SRC_SKIP=0: always load the source in the residual epilogue
     float* state[kDepth][2] = {{nullptr}};
     int cur = 0;
     int src_batch = 0, batch = 0;
@@ -141,8 +143,15 @@ struct hn_ctx {
     bool tcf_any_width = true; // fused DoubleConv kernels for every even width up to 256 (not only 32 / 64 / 128 / 256)
     int tcf_min_width = 8;
     int dconv_min_rows = 4;    // shortest strip of the fused DoubleConv kernels (small batches: more, shorter strips fill more SMs)
-    int tcd_min_res = 64;      // tensor-core down-/up-sampling for output (input) widths >= this (M = 64 MMAs at exactly 64); 32 works
-                               // too (-1 %), but the fp32 CUDA-core kernels keep a wider margin on the README RMSE-trajectory bar
+    bool fuse_bottom = true;   // decode[4] (the 8 -> 8 -> 8 DoubleConv at the bottom of the UNet) through the fused DoubleConv kernel
+    // conv_state[d] (the hidden-state update) feeds nothing else in the same iteration: with side_state its kernels run on a
+    // second stream / graph branch that forks after conv_signal[d] and joins at the end of the iteration, off the critical path
+    // (HELMNET_SIDE_STATE: 0 off, 1 on, unset: on for solves of at most kSideAutoPoints points)
+    int side_cfg = -1;
+    bool side_state = false;
+    bool side_pending = false;
+    int tcd_min_res = 16;      // tensor-core down-/up-sampling for output (input) widths >= this (M = 64 MMAs up to 64 pixels): every
+                               // level of the 256^2 pyramid (r1: 64, the 64- and 32-pixel levels ran on the CUDA cores, 0.18 ms)
     Weights W;
     // residual norms
     double* ssq = nullptr;
@@ -155,6 +164,8 @@ struct hn_ctx {
     bool use_graph = true;
 #ifndef HN_EMU
     std::map<long long, cudaGraphExec_t> graphs;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork[kDepth] = {nullptr}, ev_join = nullptr;
 #endif
     std::vector<void*> allocs;
 };
@@ -547,9 +558,36 @@ static void pack_double_conv(Packer& pk, Cursor& cur, ConvW out[2], int cin, int
 // kernel launch helpers
 // ------------------------------------------------------------------------------------------------
 constexpr long long kPdlAutoPoints = 4ll << 20;
+constexpr long long kSideAutoPoints = 4ll << 20;   // side branch for conv_state: on for small solves (measured)
 static inline void pdl_select(hn_ctx* c, int B) {
     c->pdl_mode = c->pdl_cfg >= 0 ? c->pdl_cfg : ((long long)B * c->n * c->n <= kPdlAutoPoints ? 2 : 0);
     c->pdl = c->pdl_mode != 0;
+#ifndef HN_EMU
+    c->side_state = c->side_cfg >= 0 ? c->side_cfg != 0 : ((long long)B * c->n * c->n <= kSideAutoPoints);
+#endif
+}
+// fork / join of the conv_state side branch (no-ops when it is off)
+static int side_fork(hn_ctx* c, int d, cudaStream_t st, cudaStream_t* out) {
+    *out = st;
+#ifndef HN_EMU
+    if (c->side_state) {
+        HN_CUDA(cudaEventRecord(c->ev_fork[d], st));
+        HN_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork[d], 0));
+        *out = c->side;
+        c->side_pending = true;
+    }
+#endif
+    return HN_OK;
+}
+static int side_join(hn_ctx* c, cudaStream_t st) {
+#ifndef HN_EMU
+    if (c->side_pending) {
+        HN_CUDA(cudaEventRecord(c->ev_join, c->side));
+        HN_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
+        c->side_pending = false;
+    }
+#endif
+    return HN_OK;
 }
 // Should a persistent tcgen05 kernel let its dependents in early (pdl_trigger)?  Mode 2: yes when it runs one CTA per SM or
 // when every CTA has at most one strip (a single round); a kernel that walks several rounds with two CTAs per SM keeps the
@@ -891,7 +929,7 @@ static int launch_dconv(hn_ctx* c, const ConvW (&w)[2], const float* inA, const 
 
 // HybridNet.forward (architectures.py:439-465).  `from_in6`: read the 6-channel input from c->in6 instead of
 // building it from (wf, 1e3*res, sigmas); `raw_out`: store the network output to c->dwf instead of updating wf.
-static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool raw_out) {
+static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool raw_out, bool defer_join = false) {
     const Weights& W = c->W;
     pdl_select(c, B);
     const int cur = c->cur, nxt = cur ^ 1;
@@ -930,38 +968,45 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
             Conv3Args s1 = conv_args(c, W.sig[d][1], c->mid[d], nullptr, c->skip[d], r, S_SKIP + d, S_MID + d);
             HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, s1, B, st)));
         }
+        // hidden-state update: nothing else of this iteration reads it, so it may run on the side branch (no PDL edge there)
+        cudaStream_t ss;
+        HN_TRY(side_fork(c, d, st, &ss));
+        const bool pdl_main = c->pdl;
+        if (ss != st) c->pdl = false;
         HN_TRY_DCONV(fsta, (launch_dconv<SRC_A8_B2, EPI_STORE2>(c, W.sta[d], c->skip[d], c->state[d][cur], c->state[d][nxt], r,
-                                                                 S_STATE + 2 * d + nxt, S_SKIP + d, S_STATE + 2 * d + cur, B, st)));
-        if (fsta) {
-            HN_TRY(launch_down(c, d, B, st));
-            continue;
+                                                                 S_STATE + 2 * d + nxt, S_SKIP + d, S_STATE + 2 * d + cur, B, ss)));
+        if (!fsta) {
+            Conv3Args t0 = conv_args(c, W.sta[d][0], c->skip[d], c->state[d][cur], c->mid2[d], r, -1, S_SKIP + d, S_STATE + 2 * d + cur);
+            HN_TRY((launch_conv3<SRC_A8_B2, 2, true, EPI_STORE>(c, t0, B, ss)));
+            if (c->lean_state2) {
+                State2Args s2;
+                s2.in = c->mid2[d];
+                s2.w = c->wdev + W.sta[d][1].raw;
+                s2.bias = c->wdev + W.sta[d][1].b;
+                s2.out = c->state[d][nxt];
+                s2.amax_out = c->amax + S_STATE + 2 * d + nxt;
+                s2.H = r;
+                s2.W = r;
+                HN_LAUNCH_PDL(c->pdl, state2_kernel, dim3((r + S2_TX - 1) / S2_TX, (r + S2_TY - 1) / S2_TY, B), dim3(S2_THREADS), 0, ss, s2);
+                c->launches++;
+            } else {
+                Conv3Args t1 = conv_args(c, W.sta[d][1], c->mid2[d], nullptr, c->state[d][nxt], r, S_STATE + 2 * d + nxt);
+                HN_TRY((launch_conv3<SRC_A2, 2, false, EPI_STORE>(c, t1, B, ss)));
+            }
         }
-        Conv3Args t0 = conv_args(c, W.sta[d][0], c->skip[d], c->state[d][cur], c->mid2[d], r, -1, S_SKIP + d, S_STATE + 2 * d + cur);
-        HN_TRY((launch_conv3<SRC_A8_B2, 2, true, EPI_STORE>(c, t0, B, st)));
-        if (c->lean_state2) {
-            State2Args s2;
-            s2.in = c->mid2[d];
-            s2.w = c->wdev + W.sta[d][1].raw;
-            s2.bias = c->wdev + W.sta[d][1].b;
-            s2.out = c->state[d][nxt];
-            s2.amax_out = c->amax + S_STATE + 2 * d + nxt;
-            s2.H = r;
-            s2.W = r;
-            HN_LAUNCH_PDL(c->pdl, state2_kernel, dim3((r + S2_TX - 1) / S2_TX, (r + S2_TY - 1) / S2_TY, B), dim3(S2_THREADS), 0, st, s2);
-            c->launches++;
-        } else {
-            Conv3Args t1 = conv_args(c, W.sta[d][1], c->mid2[d], nullptr, c->state[d][nxt], r, S_STATE + 2 * d + nxt);
-            HN_TRY((launch_conv3<SRC_A2, 2, false, EPI_STORE>(c, t1, B, st)));
-        }
+        c->pdl = pdl_main;
         HN_TRY(launch_down(c, d, B, st));
     }
     // bottom
     {
         const int r = c->r[kDepth];
-        Conv3Args b0 = conv_args(c, W.bot[0], c->x[kDepth], nullptr, c->mid[kDepth], r, S_MID + kDepth, S_X + kDepth);
-        HN_TRY((launch_conv3<SRC_A8, 8, true, EPI_STORE>(c, b0, B, st)));
-        Conv3Args b1 = conv_args(c, W.bot[1], c->mid[kDepth], nullptr, c->bot, r, S_BOT, S_MID + kDepth);
-        HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, b1, B, st)));
+        HN_TRY_DCONV(fbot, c->fuse_bottom ? (launch_dconv<SRC_A8, EPI_STORE>(c, W.bot, c->x[kDepth], nullptr, c->bot, r, S_BOT, S_X + kDepth, -1, B, st)) : 0);
+        if (!fbot) {
+            Conv3Args b0 = conv_args(c, W.bot[0], c->x[kDepth], nullptr, c->mid[kDepth], r, S_MID + kDepth, S_X + kDepth);
+            HN_TRY((launch_conv3<SRC_A8, 8, true, EPI_STORE>(c, b0, B, st)));
+            Conv3Args b1 = conv_args(c, W.bot[1], c->mid[kDepth], nullptr, c->bot, r, S_BOT, S_MID + kDepth);
+            HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_STORE>(c, b1, B, st)));
+        }
     }
     // decoder
     for (int d = kDepth - 1; d >= 0; d--) {
@@ -991,6 +1036,7 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
             HN_TRY((launch_conv3<SRC_A8, 8, false, EPI_OUTC>(c, d1, B, st)));
         }
     }
+    if (!defer_join) HN_TRY(side_join(c, st));
     return HN_OK;
 }
 
@@ -1033,6 +1079,7 @@ static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, co
         a.rx = reinterpret_cast<const float2*>(c->rx) + off;
         a.ksq = ksq ? ksq + off : nullptr;
         a.src = src ? reinterpret_cast<const float2*>(src) + (src_batch > 1 ? off : 0) : nullptr;
+        a.src_nz = (src != nullptr && src == c->src && c->src_skip && (n % 8) == 0) ? c->src_nz + (src_batch > 1 ? (size_t)b0 * n : 0) : nullptr;
         a.res = reinterpret_cast<float2*>(res) + off;
         a.ssq = ssq;
         a.slot = slot;
@@ -1057,8 +1104,9 @@ static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, co
 }
 
 static int launch_iteration(hn_ctx* c, int B, cudaStream_t st) {
-    HN_TRY(launch_unet(c, B, st, false, false));
+    HN_TRY(launch_unet(c, B, st, false, false, true));
     HN_TRY(launch_spectral(c, B, st, c->wf, c->ksq, c->src, c->src_batch, c->res, c->ssq, c->iter_dev, c->amax + S_RES + (c->cur ^ 1)));
+    HN_TRY(side_join(c, st));      // the conv_state branch joins after the residual stage
     HN_LAUNCH_PDL(c->pdl, advance_iter_kernel, dim3(1), dim3(32), 0, st, c->iter_dev);
     c->launches++;
     return HN_OK;
@@ -1133,6 +1181,7 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     A_(c->ksq, B * hw);
     A_(c->src, B * hw * 2);
     A_(c->rx, B * hw * 2);
+    A_(c->src_nz, B * (size_t)n + 16);
     A_(c->tmp2, B * hw * 2);
     A_(c->tmp2b, B * hw * 2);
     A_(c->dwf, B * hw * 2);
@@ -1164,6 +1213,15 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     if (const char* mr = getenv("HELMNET_TCR_MIN_RES")) c->tcr_min_res = atoi(mr);
     if (const char* mr = getenv("HELMNET_TCD_MIN_RES")) c->tcd_min_res = atoi(mr);
     if (const char* pv = getenv("HELMNET_PDL")) c->pdl_cfg = atoi(pv);
+    if (const char* pv = getenv("HELMNET_SRC_SKIP")) c->src_skip = atoi(pv) != 0;
+    if (const char* pv = getenv("HELMNET_FUSE_BOTTOM")) c->fuse_bottom = atoi(pv) != 0;
+    if (const char* pv = getenv("HELMNET_SIDE_STATE")) c->side_cfg = atoi(pv);
+#ifndef HN_EMU
+    if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail(HN_ERR_CUDA, "cudaStreamCreate failed"));
+    for (int d = 0; d < kDepth; d++)
+        if (cudaEventCreateWithFlags(&c->ev_fork[d], cudaEventDisableTiming) != cudaSuccess) return cleanup(fail(HN_ERR_CUDA, "cudaEventCreate failed"));
+    if (cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) return cleanup(fail(HN_ERR_CUDA, "cudaEventCreate failed"));
+#endif
     if (const char* pv = getenv("HELMNET_TCF_ANY_WIDTH")) c->tcf_any_width = atoi(pv) != 0;
     if (const char* pv = getenv("HELMNET_TCF_MIN_WIDTH")) c->tcf_min_width = atoi(pv);
     if (const char* pv = getenv("HELMNET_DCONV_MIN_ROWS")) { const int v = atoi(pv); if (v >= 2 && v % 2 == 0) c->dconv_min_rows = v; }
@@ -1191,6 +1249,10 @@ int hn_destroy(hn_ctx* c) {
 #ifndef HN_EMU
     cudaDeviceSynchronize();
     for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    if (c->side) cudaStreamDestroy(c->side);
+    for (int d = 0; d < kDepth; d++)
+        if (c->ev_fork[d]) cudaEventDestroy(c->ev_fork[d]);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
 #endif
     for (void* p : c->allocs) cudaFree(p);
     if (c->ssq) cudaFree(c->ssq);
@@ -1204,6 +1266,7 @@ int hn_load_weights(hn_ctx* c, const float* host_blob, size_t n_floats) {
     if (n_floats != HN_NUM_WEIGHTS) return fail(HN_ERR_ARG, "expected 48160 floats (HybridNet features=8 depth=4 state=2)");
     Packer pk;
     Cursor cur{host_blob, n_floats};
+    c->W = Weights();      // per-layer norms (ConvW::l1 / bmax) are running maxima: start from zero on every load
     Weights& W = c->W;
     pack_double_conv(pk, cur, W.inc, 6, 8, 8);
     for (int d = 0; d < kDepth; d++) {   // module order inside EncoderBlock: conv_signal, down, conv_state
@@ -1266,6 +1329,11 @@ int hn_set_source(hn_ctx* c, const float* d_src, int src_batch, const int64_t st
               reinterpret_cast<float2*>(c->src), c->n, total, (long long)strides[0], (long long)strides[1],
               (long long)strides[2], (long long)strides[3]);
     c->launches++;
+    {
+        const int cols = src_batch * c->n;
+        HN_LAUNCH(src_colnz_kernel, dim3((cols + 127) / 128), dim3(128), 0, st, reinterpret_cast<const float2*>(c->src), c->src_nz, c->n, cols);
+        c->launches++;
+    }
     HN_CUDA(cudaGetLastError());
     c->src_batch = src_batch;
     return HN_OK;
@@ -1411,8 +1479,9 @@ int hn_get_states(hn_ctx* c, float* d_hflat, int batch, void* stream) {
 
 #ifndef HN_EMU
 static int get_graph(hn_ctx* c, int B, cudaGraphExec_t* out) {
+    pdl_select(c, B);     // launch options that depend on the batch (PDL mode, side branch) are part of the graph
     // the source pointer offset / broadcast flag are baked into the spectral kernel's parameters: part of the key
-    const long long key = ((long long)B << 9) | ((long long)(c->src_batch > 1 ? 1 : 0) << 8) | ((long long)c->cur << 4) | (long long)c->engine;
+    const long long key = ((long long)B << 10) | ((long long)(c->side_state ? 1 : 0) << 9) | ((long long)(c->src_batch > 1 ? 1 : 0) << 8) | ((long long)c->cur << 4) | (long long)c->engine;
     auto it = c->graphs.find(key);
     if (it != c->graphs.end()) {
         *out = it->second;
@@ -1471,6 +1540,7 @@ int hn_run(hn_ctx* c, int n_iters, float* d_rmse, float* d_wf_hist, float* d_res
     HN_CUDA(cudaMemsetAsync(c->ssq, 0, need * sizeof(double), st));
     HN_CUDA(cudaMemsetAsync(c->iter_dev, 0, sizeof(int), st));
     const size_t total = (size_t)B * hw;
+    pdl_select(c, B);
     for (int it = 0; it < n_iters; it++) {
 #ifndef HN_EMU
         if (c->use_graph) {
@@ -1672,6 +1742,7 @@ int hn_profile_layer(hn_ctx* c, int which, int reps, float* out_ms, void* stream
                     a.rx = reinterpret_cast<const float2*>(c->rx);
                     a.ksq = c->ksq;
                     a.src = reinterpret_cast<const float2*>(c->src);
+                    a.src_nz = c->src_skip ? c->src_nz : nullptr;
                     a.res = reinterpret_cast<float2*>(c->tmp2b);
                     a.ssq = nullptr;
                     a.slot = c->iter_dev + 1;
@@ -1707,9 +1778,10 @@ int hn_profile_layer(hn_ctx* c, int which, int reps, float* out_ms, void* stream
                                                             S_STATE + (cur ^ 1), S_SKIP + 0, S_STATE + cur, B, st);
                 rc = f == 1 ? HN_OK : (f < 0 ? f : fail(HN_ERR_STATE, "fused DoubleConv kernel not available for this level/engine"));
             } break;
-            case 9: {   // decode[0] + outc, raw output to the scratch dwf buffer (the wavefield is not touched)
+            case 9: {   // decode[0] + outc + wavefield update, exactly the launch of the iteration (reads and rewrites wf: the solve
+                        // state is disturbed, callers reset afterwards)
                 int f = launch_dconv<SRC_A8_B8, EPI_OUTC>(c, W.dec[0], c->upo[0], c->skip[0], c->dec[0], c->r[0], -1, S_UPO + 0, S_SKIP + 0, B, st,
-                                                          &W.outc, c->wf, c->dwf);
+                                                          &W.outc, c->wf, nullptr);
                 rc = f == 1 ? HN_OK : (f < 0 ? f : fail(HN_ERR_STATE, "fused DoubleConv kernel not available for this level/engine"));
             } break;
 #endif

@@ -219,6 +219,7 @@ struct ColsArgs {
     const float2* rx;     // [B][n][n]  row-axis part
     const float* ksq;     // [B][n][n] or null
     const float2* src;    // [src_batch][n][n] or null
+    const unsigned char* src_nz;   // [src_batch][n] or null: 1 where column j of the source map holds a non-zero (src_colnz_kernel)
     float2* res;          // [B][n][n]
     double* ssq;          // [slots][B] or null
     const int* slot;      // device scalar: which ssq slot (iteration index)
@@ -226,6 +227,32 @@ struct ColsArgs {
     int src_batch, B, CW;
     int b0;               // first sample of this launch (ssq is indexed by the absolute sample)
 };
+
+// Point sources are zero almost everywhere: one flag per (source map, column) lets a column tile skip the source loads
+// of the residual epilogue altogether (subtracting an exact zero changes nothing, so results are bit-identical).
+__global__ void src_colnz_kernel(const float2* __restrict__ src, unsigned char* __restrict__ nz, int n, int total_cols) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total_cols) return;
+    const int s = idx / n, j = idx - s * n;
+    const float2* p = src + (size_t)s * n * n + j;
+    bool any = false;
+    for (int i = 0; i < n; i++) {
+        const float2 v = p[(size_t)i * n];
+        any = any || !(v.x == 0.f && v.y == 0.f);
+    }
+    nz[idx] = any ? 1 : 0;
+}
+// source pointer of the 8-column tile starting at column j0 of sample `b` (relative to the launch), or null when the
+// whole tile of the source map is zero
+__device__ __forceinline__ const float2* tile_source(const ColsArgs& a, int b, int n, int j0) {
+    if (a.src == nullptr) return nullptr;
+    const size_t sb = a.src_batch > 1 ? (size_t)b : (size_t)0;
+    if (a.src_nz != nullptr) {
+        const unsigned long long f = *reinterpret_cast<const unsigned long long*>(a.src_nz + sb * n + j0);   // 8 flags, j0 % 8 == 0
+        if (f == 0ull) return nullptr;
+    }
+    return a.src + sb * (size_t)n * n + j0;
+}
 
 __global__ void __launch_bounds__(SPEC_THREADS) spectral_cols_kernel(SpecTables t, ColsArgs a) {
     HN_DYN_SMEM(float2, smem_sp);

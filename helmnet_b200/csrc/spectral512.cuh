@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(THREADS) spectral_cols512_kernel(SpecTables t,
     __syncthreads();
     float part = 0.f, lmax = 0.f;
     constexpr int EPI_CHUNK = 8;
-    const float2* srcp = a.src != nullptr ? a.src + (a.src_batch > 1 ? img : (size_t)0) + j0 : nullptr;
+    const float2* srcp = tile_source(a, b, N, j0);
 #pragma unroll 1
     for (int it0 = threadIdx.x; it0 < N * LINES; it0 += THREADS * EPI_CHUNK) {
         float2 sv[EPI_CHUNK], rxv[EPI_CHUNK];

@@ -136,7 +136,7 @@ int hn_sync_check(hn_ctx* ctx, void* stream);
 /* Average device time in ms of `reps` launches of one kernel of the iteration on the current buffers
  * (which = 0 inc conv #2, 1 decode[0] conv #1 [engine-1 single-conv kernels], 2 enc[0].down, 3 up[0], 4 spectral rows,
  * 5 spectral cols, and the fused DoubleConv kernels of level 0 [engine 2]: 6 inc, 7 enc[0].conv_signal,
- * 8 enc[0].conv_state, 9 decode[0] + outc). Synchronous. */
+ * 8 enc[0].conv_state, 9 decode[0] + outc + wavefield update -- this one rewrites the wavefield: reset afterwards). Synchronous. */
 int hn_profile_layer(hn_ctx* ctx, int which, int reps, float* out_ms, void* stream);
 /* Per-stage device time of the last hn_profile_iteration() in milliseconds:
  * out[0] = UNet stage, out[1] = spectral residual stage. Synchronous; runs ONE iteration. */

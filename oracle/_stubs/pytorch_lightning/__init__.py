@@ -28,11 +28,26 @@ class LightningModule(nn.Module):
             if name != "self":
                 self.hparams[name] = args.locals[name]
 
+    # Lightning's DeviceDtypeModuleMixin remembers the device the module was moved to (it does not look at the parameters):
+    # the reference relies on that in set_domain_size, where the freshly built source parameter still sits on the CPU when
+    # `self.Lap.to(self.device)` runs (hybridnet.py:92-101).
     @property
     def device(self):
-        for p in self.parameters():
-            return p.device
-        return torch.device("cpu")
+        return getattr(self, "_stub_device", torch.device("cpu"))
+
+    def to(self, *args, **kwargs):
+        out = torch._C._nn._parse_to(*args, **kwargs)
+        if out[0] is not None:
+            self._stub_device = out[0]
+        return super().to(*args, **kwargs)
+
+    def cuda(self, device=None):
+        self._stub_device = torch.device("cuda", torch.cuda.current_device() if device is None else (device if isinstance(device, int) else torch.device(device).index or 0))
+        return super().cuda(device)
+
+    def cpu(self):
+        self._stub_device = torch.device("cpu")
+        return super().cpu()
 
     def freeze(self):
         for p in self.parameters():

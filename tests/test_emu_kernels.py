@@ -13,7 +13,7 @@ def test_laplacian(emu_solver, gold, n):
     g = gold(f"operator_n{n}.npz")
     emu_solver.set_domain_size(n, source_location=[n // 3, n // 2])
     assert rel_l2(emu_solver.Lap(torch.tensor(g["u"])), g["Lu"]) < 1e-6
-    assert torch.equal(emu_solver.source, torch.tensor(g["source"]))
+    assert rel_l2(emu_solver.source, g["source"]) < 1e-6       # hn_point_sources writes the exact map (the reference carries 4e-7 of FFT noise)
 
 
 def test_laplacian_generic_radix(emu_solver):

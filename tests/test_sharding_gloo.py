@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from helmnet_b200.sharding import gather_results, shard_slice
+from helmnet_b200.sharding import gather_results, shard_sizes, shard_slice
 
 
 def test_shard_slice_covers_batch():
@@ -26,10 +26,15 @@ def _worker(rank, world, port, q):
     full_wf = torch.arange(batch * 2 * n * n, dtype=torch.float32).reshape(batch, 2, n, n)
     full_rm = torch.arange(k * batch, dtype=torch.float32).reshape(k, batch)
     out = gather_results(full_wf[lo:hi].clone(), full_rm[:, lo:hi].clone(), dst=0)
+    # known slice sizes (no size exchange), and the equal-slice fast path (batch 4 over 2 ranks)
+    out2 = gather_results(full_wf[lo:hi].clone(), full_rm[:, lo:hi].clone(), dst=0, sizes=shard_sizes(batch, world))
+    lo4, hi4 = shard_slice(4, world, rank)
+    out3 = gather_results(full_wf[lo4:hi4].clone(), full_rm[:, lo4:hi4].clone(), dst=0, sizes=shard_sizes(4, world))
     if rank == 0:
-        q.put((torch.equal(out[0], full_wf), torch.equal(out[1], full_rm)))
+        ok = torch.equal(out[0], full_wf) and torch.equal(out2[0], full_wf) and torch.equal(out3[0], full_wf[:4])
+        q.put((ok, torch.equal(out[1], full_rm) and torch.equal(out2[1], full_rm) and torch.equal(out3[1], full_rm[:, :4])))
     else:
-        assert out is None
+        assert out is None and out2 is None and out3 is None
     dist.destroy_process_group()
 
 

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out; out=gpurun_out/r2_first.txt; : > $out
 rm -f gpurun_out/parity_measured.jsonl
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv >> $out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/tests_r2_first.log 2>&1
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/tests_r2_first.log 2>&1
 echo "tests rc=$?  $(tail -1 gpurun_out/tests_r2_first.log)" | tee -a $out
 grep -E "^FAILED|^E  " gpurun_out/tests_r2_first.log | head -30 >> $out
 timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_r2_first.json 2> gpurun_out/bench_r2_first.err
@@ -29,6 +29,10 @@ HELMNET_PDL=0 $q 256x32 256x64 --tag pdl0 >> $out 2>&1
 HELMNET_PDL=1 $q 256x32 256x64 256x256 --tag pdl1 >> $out 2>&1
 HELMNET_PDL=2 $q 256x64 256x256 --tag pdl2 >> $out 2>&1
 HELMNET_DCONV_MIN_ROWS=8 $q 256x32 --tag minrows8 >> $out 2>&1
+HELMNET_FUSE_BOTTOM=0 $q 256x256 256x32 256x1 --tag nofusebottom >> $out 2>&1
+HELMNET_SRC_SKIP=0 $q 256x256 256x32 --tag nosrcskip >> $out 2>&1
+HELMNET_SIDE_STATE=1 $q 256x256 256x64 256x32 256x16 256x1 96x32 --tag side_state >> $out 2>&1
+HELMNET_SIDE_STATE=1 HELMNET_PDL=1 $q 256x32 --tag side_state_pdl1 >> $out 2>&1
 # ncu: launch list of the bench command (serialised, cold cache), then a full capture with source of one iteration
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-extras --residual-iters 0"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv $B > gpurun_out/ncu_launch.log 2>&1

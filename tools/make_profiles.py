@@ -6,7 +6,7 @@
     ncu --set full --clock-control none --import-source on -k regex:"dconv_tcf|spectral|down_tcr|up_tcr" -s 14 -c 14 \\
         -o gpurun_out/prof_e2 -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --residual-iters 0
     ncu -i gpurun_out/prof_e2.ncu-rep --page raw --csv > gpurun_out/prof_e2_raw.csv
-    python tools/make_profiles.py gpurun_out/launches_e2.csv gpurun_out/prof_e2_raw.csv <bench ms per iteration>
+    python tools/make_profiles.py gpurun_out/launches_e2.csv gpurun_out/prof_e2_raw.csv <bench ms per iteration> [r2]
 """
 import csv
 import json
@@ -15,6 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SMS = 148
+PREFIX = sys.argv[4] if len(sys.argv) > 4 else 'r1'       # round prefix of the files written under profiles/
 
 
 def launches(path, bench_us):
@@ -26,8 +27,9 @@ def launches(path, bench_us):
             continue
         if hdr and len(r) == len(hdr):
             data.append(dict(zip(hdr, r)))
-    idx = [i for i, d in enumerate(data) if 'advance_iter' in d['Kernel Name']]
-    a, b = idx[-2], idx[-1]
+    # the last complete iteration: from the reset_amax_kernel that opens it to the advance_iter_kernel that closes it
+    b = [i for i, d in enumerate(data) if 'advance_iter' in d['Kernel Name']][-1]
+    a = [i for i, d in enumerate(data[:b]) if 'reset_amax' in d['Kernel Name']][-1] - 1
     out = ["# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3` (256^2 x 256, engine 2), one B200.",
            "# One solver iteration = the launches between two advance_iter_kernel launches (replayed as one CUDA graph in production).",
            "# Per-launch times are cold-cache and serialised by ncu: the kernel's SHARE of the iteration is what compares with bench.py.",
@@ -37,7 +39,7 @@ def launches(path, bench_us):
         t = float(d['Metric Value'].replace(',', '')) / 1e3
         out.append(f"{d['Kernel Name'][:64]:64s} {d['Grid Size']:14s} {d['Block Size']:12s} {t:8.1f} {100 * t / tot:5.1f}%")
     out.append(f"# total {tot:.1f} us per iteration under ncu ({b - a} launches); bench.py (graph replay, warm): {bench_us:.0f} us")
-    open(os.path.join(ROOT, 'profiles', 'r1_launches_engine2.txt'), 'w').write("\n".join(out) + "\n")
+    open(os.path.join(ROOT, 'profiles', f'{PREFIX}_launches_engine2.txt'), 'w').write("\n".join(out) + "\n")
 
 
 def full(path):
@@ -56,7 +58,7 @@ def full(path):
             ('tensor%', 'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed'),
             ('issue%', 'smsp__issue_active.avg.pct_of_peak_sustained_active'), ('regs', 'launch__registers_per_thread'),
             ('warps%', 'sm__warps_active.avg.pct_of_peak_sustained_active'), ('utcmma', 'smsp__sass_inst_executed_op_utcmma.sum')]
-    out = ["# ncu --set full --clock-control none, one launch of each level-0/1 kernel of the engine-2 iteration, 256^2 x 256, one B200 (r1 final).",
+    out = ["# ncu --set full --clock-control none, one launch of each level-0/1 kernel of the engine-2 iteration, 256^2 x 256, one B200.",
            "# smem model: the SM's shared memory moves one 128-byte wavefront per cycle for ALL clients; wavefronts per SM =",
            "#   (tcgen05 operand reads + LSU wavefronts without bank-conflict replays + TMA fill bytes/128) ~ elapsed cycles for the fused",
            "#   DoubleConv kernels, i.e. they run at the shared-memory bandwidth roofline (see DESIGN.md 4.2).", ""]
@@ -98,14 +100,14 @@ def full(path):
                 out.append(f"   -> {n_mma:,.0f} tcgen05.mma per SM, {cyc / n_mma:.1f} cycles per MMA (44.5 in isolation, tools/tc_bench.cu)")
         except (KeyError, ValueError):
             pass
-    open(os.path.join(ROOT, 'profiles', 'r1_ncu_full_engine2.txt'), 'w').write("\n".join(out) + "\n")
+    open(os.path.join(ROOT, 'profiles', f'{PREFIX}_ncu_full_engine2.txt'), 'w').write("\n".join(out) + "\n")
     for i, (_, v) in best.items():
         traffic[i] = v
     doc = {"config": {"n": 256, "batch_per_gpu": 256},
-           "source": "ncu --set full --clock-control none, profiles/r1_ncu_full_engine2.txt (dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+           "source": f"ncu --set full --clock-control none, profiles/{PREFIX}_ncu_full_engine2.txt (dram__bytes_read.sum + dram__bytes_write.sum per launch, "
                      "in-iteration launches)",
            "kernels": {str(k): v for k, v in sorted(traffic.items())}}
-    json.dump(doc, open(os.path.join(ROOT, 'profiles', 'r1_dram_traffic.json'), 'w'), indent=1)
+    json.dump(doc, open(os.path.join(ROOT, 'profiles', f'{PREFIX}_dram_traffic.json'), 'w'), indent=1)
 
 
 if __name__ == '__main__':

@@ -16,7 +16,7 @@ from helmnet_b200 import IterativeSolver  # noqa: E402
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    args = [a for a in sys.argv[1:] if "x" in a and a.replace("x", "").isdigit()]
     iters = int(sys.argv[sys.argv.index("--iters") + 1]) if "--iters" in sys.argv else 50
     tag = sys.argv[sys.argv.index("--tag") + 1] if "--tag" in sys.argv else ""
     dev = torch.device("cuda", 0)
