@@ -179,23 +179,28 @@ def test_readme_full_iteration_count(cuda_solver, gold):
     assert abs(float(wf.double().norm()) - 55.10) < 0.01 and abs(float(wf.abs().max()) - 2.547) < 1e-3
 
 
-def test_c4_full_iteration_count(cuda_solver, gold):
-    """A C4-style map (512^2, thick skull-like outline + heterogeneity, source [450,256]) at the configuration's K = 3000
-    (support_functions.py:328-333).  The literal 8(d) C4 recipe (boost 0.9..1.0) makes the reference itself diverge
-    (oracle/make_golden_r2.py: c4_style_map), so the fixture keeps the outline and the training range of the contrast."""
+def test_c4_style_map_k1000(cuda_solver, gold):
+    """A C4-style map (512^2, thick skull-like outline + heterogeneity, source [450,256]), 1000 iterations.  The literal 8(d) C4
+    recipe (boost 0.9..1.0) makes the reference itself diverge, and at the configuration's K = 3000
+    (support_functions.py:328-333) the reference is not reproducible against itself (sporadic residual bursts on the round-off
+    plateau at different iterations in its fp32 and fp64 runs, final wavefields 1.7e-2 apart: oracle/make_golden_r2.py, fx_c4),
+    so the fixture keeps the outline with the training range of the contrast and stops at 1000 iterations."""
     if cuda_solver._engine == 0:
-        pytest.skip("3000 iterations at 512^2 on the fp32 CUDA-core engine take minutes; engines 1 and 2 cover the path")
-    g = gold("traj_c4_n512_k3000.npz")
+        pytest.skip("1000 iterations at 512^2 on the fp32 CUDA-core engine take a while; engines 1 and 2 cover the path")
+    g = gold("traj_c4_n512_k1000.npz")
     s = cuda_solver
     s.set_domain_size(512, source_location=[450, 256])
-    out = s.forward(torch.tensor(g["sos"]).cuda(), num_iterations=3000, return_residuals=False)
+    out = s.forward(torch.tensor(g["sos"]).cuda(), num_iterations=1000, return_residuals=False)
     wf = out["wavefields"][0]
     rm = out["residual_rmse"].cpu().numpy()[:, 0]
-    e_wf = rel_l2(wf, g["wavefield"])
-    e_rm = rel_l2(rm, g["rmse"])
-    record("c4_k3000", engine=s._engine, final_vs_ref32=e_wf, final_vs_fp64=rel_l2(wf, g["wavefield64"]),
-           ref32_vs_fp64=rel_l2(g["wavefield"], g["wavefield64"]), rmse_traj_rel_l2=e_rm, rmse_last=float(rm[-1]), ref_rmse_last=float(g["rmse"][-1]))
-    assert e_wf < FINAL_TOL and e_rm < FINAL_TOL, (e_wf, e_rm)
+    e_wf, e_wf64, ref64 = rel_l2(wf, g["wavefield"]), rel_l2(wf, g["wavefield64"]), rel_l2(g["wavefield"], g["wavefield64"])
+    e_head = float(np.max(np.abs(rm[:300] - g["rmse"][:300]) / g["rmse"][:300]))
+    record("c4_style_k1000", engine=s._engine, final_vs_ref32=e_wf, final_vs_fp64=e_wf64, ref32_vs_fp64=ref64, rmse_head_max_rel=e_head,
+           rmse_traj_rel_l2=rel_l2(rm, g["rmse"]), rmse_last=float(rm[-1]), ref_rmse_last=float(g["rmse"][-1]))
+    assert e_head < FINAL_TOL and rel_l2(rm, g["rmse"]) < FINAL_TOL, (e_head, rel_l2(rm, g["rmse"]))
+    # final wavefield: the 1e-3 bar, or twice the reference's own fp32-vs-fp64 distance where that is already beyond it
+    assert e_wf64 <= max(FINAL_TOL, 2.0 * ref64), (e_wf64, ref64)
+    assert e_wf <= max(FINAL_TOL, 3.0 * ref64), (e_wf, ref64)
 
 
 def test_trajectory_source_maps_golden(cuda_solver, gold):

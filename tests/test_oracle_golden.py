@@ -146,15 +146,19 @@ def test_readme_full_iteration_count(gold, f_weights):
     assert rel_l2(g["wavefield"], g["wavefield64"]) < 1e-3          # measured: 3.6e-4
 
 
-def test_c4_fixture_head(gold, f_weights):
-    """C4-style 512^2 map: first 40 iterations of the oracle against the reference's K = 3000 run (the full count is the GPU test)."""
-    from helmnet_b200.synthetic import config_sos
-    g = gold("traj_c4_n512_k3000.npz")
-    assert np.array_equal(config_sos("C4", 1).numpy(), g["sos"])
+def test_c4_style_fixture(gold, f_weights):
+    """C4-style 512^2 map: first 40 iterations of the oracle against the reference's run, and the record of why K = 3000 is no
+    parity target (bursts on the round-off plateau at different iterations in the reference's fp32 and fp64 runs)."""
+    g = gold("traj_c4_n512_k1000.npz")
     orc = O.Oracle(f_weights, 512)
     orc.set_source(O.point_source(512, [450, 256]))
     out = orc.forward(torch.tensor(g["sos"]), 40)
     assert rel_l2(out["rmse"][:, 0], g["rmse"][:40]) < 1e-5
+    assert np.max(np.abs(g["rmse"][:600] - g["rmse64"][:600]) / g["rmse64"][:600]) < 1e-2       # the two precisions agree up to the plateau
+    if "rmse_k3000" in g:
+        r32, r64 = g["rmse_k3000"], g["rmse64_k3000"]
+        assert np.allclose(r32[:1000], g["rmse"], rtol=1e-6) and r32[1000:].max() > 100 * np.median(r32[1000:])   # fp32 burst (it 2532)
+        assert r64[1000:].max() > 100 * np.median(r64[1000:]) and int(r32.argmax()) != int(r64.argmax())           # fp64 burst elsewhere
 
 
 def test_variable_source(gold, f_weights):
