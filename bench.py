@@ -533,7 +533,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_point": bpp,
                          "peak_source": f"{peaks['source']} (MEASURED_PEAKS.json hbm_gbs, burst copy)"})
         cpu, gpu_eager = None, None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only (the reference arm covers every N)
             threads = os.cpu_count() or 1
             v, ms_c, kind = reference_throughput(n, args.cpu_batch, args.cpu_iters, 2, threads)
             cpu = {"value": v, "unit": "Mpoint-iterations/s", "cores": threads, "kind": kind, "ms_per_step": ms_c,

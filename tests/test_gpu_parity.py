@@ -197,7 +197,10 @@ def test_c4_style_map_k1000(cuda_solver, gold):
     e_head = float(np.max(np.abs(rm[:300] - g["rmse"][:300]) / g["rmse"][:300]))
     record("c4_style_k1000", engine=s._engine, final_vs_ref32=e_wf, final_vs_fp64=e_wf64, ref32_vs_fp64=ref64, rmse_head_max_rel=e_head,
            rmse_traj_rel_l2=rel_l2(rm, g["rmse"]), rmse_last=float(rm[-1]), ref_rmse_last=float(g["rmse"][-1]))
-    assert e_head < FINAL_TOL and rel_l2(rm, g["rmse"]) < FINAL_TOL, (e_head, rel_l2(rm, g["rmse"]))
+    # RMSE history: pointwise on the first 300 iterations; on the round-off plateau the reference's own fp32 and fp64 histories
+    # differ by 4.6e-3 (rel-L2 of the whole history, up to 39 % pointwise), which is the yardstick there
+    rm_ref64 = rel_l2(g["rmse"], g["rmse64"])
+    assert e_head < FINAL_TOL and rel_l2(rm, g["rmse"]) <= max(FINAL_TOL, rm_ref64), (e_head, rel_l2(rm, g["rmse"]), rm_ref64)
     # final wavefield: the 1e-3 bar, or twice the reference's own fp32-vs-fp64 distance where that is already beyond it
     assert e_wf64 <= max(FINAL_TOL, 2.0 * ref64), (e_wf64, ref64)
     assert e_wf <= max(FINAL_TOL, 3.0 * ref64), (e_wf, ref64)
