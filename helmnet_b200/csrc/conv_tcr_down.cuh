@@ -34,7 +34,7 @@ using tcr::mbar_arrive;
 using tcr::mbar_arrive_expect_tx;
 using tcr::tma_load_1d;
 
-constexpr int ROWS_O = 32;                 // output rows per strip
+constexpr int ROWS_O = 32;                 // default output rows per strip (Args::rows_o is picked per launch by the host)
 constexpr int NC = 16;                     // accumulator columns per output row
 constexpr int SRP = 2;                     // operand ring depth (input row pairs)
 constexpr int NSP = 2;                     // staging ring depth (input row pairs) for images wider than 128 pixels
@@ -59,6 +59,7 @@ struct Args {
     int pdl_trig;               // PDL: let the next kernel's CTAs become resident as this grid's CTAs exit (hn_ctx::pdl)
     float w_inv_scale;
     int H, W;                   // input resolution
+    int rows_o;                 // output rows per strip: small batches take short strips so that every SM gets one
     int nsx, nsy, total_strips;
 };
 
@@ -71,8 +72,8 @@ __device__ __forceinline__ Strip strip_of(int st, const Args& a) {
     const int sx = st % a.nsx, r = st / a.nsx;
     const int sy = r % a.nsy, b = r / a.nsy;
     g.ox0 = sx * CW;
-    g.oy0 = sy * ROWS_O;
-    g.Ro = min(ROWS_O, (a.H >> 1) - g.oy0);
+    g.oy0 = sy * a.rows_o;
+    g.Ro = min(a.rows_o, (a.H >> 1) - g.oy0);
     g.NP = g.Ro + 3;            // input row pairs: rows k = 0 .. 2 Ro + 5, image row 2 oy0 - 3 + k
     g.img_in = (size_t)b * a.H * a.W;
     g.img_out = (size_t)b * (a.H >> 1) * (a.W >> 1);

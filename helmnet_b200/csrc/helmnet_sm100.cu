@@ -764,7 +764,26 @@ static int launch_down(hn_ctx* c, int d, int B, cudaStream_t st) {
         t.H = r;
         t.W = r;
         t.nsx = (r / 2 + tcr::CW - 1) / tcr::CW;
-        t.nsy = (r / 2 + tcd::ROWS_O - 1) / tcd::ROWS_O;
+        {
+            // output rows per strip: whole rounds of equal strips over two CTAs per SM; a strip of R output rows streams
+            // R + 3 input row pairs (+ ~2 steps of pipeline fill).  Small batches get short strips (one per CTA slot) instead
+            // of the fixed 32 rows of r1 -- 256^2 x 32: down[0..3] 41 / 30 / 29 / 19 us on 128 / 64 / 32 / 32 CTAs before.
+            const int Ho = r / 2;
+            int best = tcd::ROWS_O;
+            long long best_cost = -1;
+            const int env_rows = getenv("HELMNET_DOWN_ROWS") ? atoi(getenv("HELMNET_DOWN_ROWS")) : 0;
+            for (int rows = 2; rows <= 128 && rows <= (Ho > 2 ? Ho : 2); rows += 2) {
+                const long long total = (long long)t.nsx * ((Ho + rows - 1) / rows) * B;
+                const long long g = total < 2 * c->num_sms ? total : 2 * c->num_sms;
+                const long long cost = ((total + g - 1) / g) * (rows + 5);
+                if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = rows; }
+            }
+            // with 64+ output rows per SM the kernel is throughput-bound and what counts is the work per SM, not per CTA slot:
+            // the 32-row strips of r1 balance best there (256^2 x 256: 175 us against 185 us with one 128-row strip per sample)
+            if ((long long)B * Ho / c->num_sms >= 64) best = Ho < tcd::ROWS_O ? Ho : tcd::ROWS_O;
+            t.rows_o = env_rows >= 1 ? env_rows : best;
+        }
+        t.nsy = (r / 2 + t.rows_o - 1) / t.rows_o;
         t.total_strips = t.nsx * t.nsy * B;
         const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;
         t.pdl_trig = pdl_early(c, t.total_strips, 2);
@@ -815,7 +834,7 @@ static int launch_up(hn_ctx* c, int d, int B, cudaStream_t st) {
             int best = tcu::ROWS_I;
             long long best_cost = -1;
             const int env_rows = getenv("HELMNET_UP_ROWS") ? atoi(getenv("HELMNET_UP_ROWS")) : 0;
-            for (int rows = 8; rows <= 128 && rows <= t.Hi; rows += 2) {
+            for (int rows = 2; rows <= 128 && rows <= t.Hi; rows += 2) {      // (r1 started at 8: too few strips for small batches)
                 if (t.Hi % rows != 0) continue;
                 const long long total = (long long)t.nsx * (t.Hi / rows) * B;
                 const long long g = total < c->num_sms ? total : c->num_sms;
