@@ -134,7 +134,7 @@ struct hn_ctx {
     // Programmatic dependent launch for the kernels of an iteration (common.cuh: HN_LAUNCH_PDL).  pdl_mode (HELMNET_PDL):
     // 0 off; 1 every kernel triggers its dependents early; 2 the persistent tcgen05 kernels that run several rounds of
     // strips with TWO CTAs per SM do not (pdl_early()); 3 no tcgen05 kernel triggers early.  Unset (pdl_cfg = -1): mode 2
-    // for solves of at most kPdlAutoPoints points, off above -- measured on B200 (tools/gpu_ab_pdl.sh): 256^2 x 1 -12 %,
+    // for solves of at most kPdlAutoPoints points, off above -- measured on B200 (tools/gpu_ab_pdl.sh, r1): 256^2 x 1 -12 %,
     // 128^2 x 64 -5 %, 96^2 x 32 -3.5 % per iteration, but nothing (+-0.5 %) at 256^2 x 256 / 512^2 x 64 / 1024^2 x 8, where
     // every kernel runs for 100+ us and the iteration is power-capped.  pdl / pdl_mode are the values in effect (pdl_select).
     int pdl_cfg = -1;
@@ -557,8 +557,8 @@ static void pack_double_conv(Packer& pk, Cursor& cur, ConvW out[2], int cin, int
 // ------------------------------------------------------------------------------------------------
 // kernel launch helpers
 // ------------------------------------------------------------------------------------------------
-constexpr long long kPdlAutoPoints = 4ll << 20;
-constexpr long long kSideAutoPoints = 4ll << 20;   // side branch for conv_state: on for small solves (measured)
+constexpr long long kPdlAutoPoints = 8ll << 20;      // r2: 256^2 x 128 1.342 -> 1.306 ms with PDL mode 2 + side branch, nothing at x 256
+constexpr long long kSideAutoPoints = 8ll << 20;   // side branch for conv_state: on for small solves (measured)
 static inline void pdl_select(hn_ctx* c, int B) {
     c->pdl_mode = c->pdl_cfg >= 0 ? c->pdl_cfg : ((long long)B * c->n * c->n <= kPdlAutoPoints ? 2 : 0);
     c->pdl = c->pdl_mode != 0;
@@ -948,7 +948,7 @@ static int launch_dconv(hn_ctx* c, const ConvW (&w)[2], const float* inA, const 
 
 // HybridNet.forward (architectures.py:439-465).  `from_in6`: read the 6-channel input from c->in6 instead of
 // building it from (wf, 1e3*res, sigmas); `raw_out`: store the network output to c->dwf instead of updating wf.
-static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool raw_out, bool defer_join = false) {
+static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool raw_out, bool defer_join = false, int* advance_slot = nullptr) {
     const Weights& W = c->W;
     pdl_select(c, B);
     const int cur = c->cur, nxt = cur ^ 1;
@@ -960,7 +960,7 @@ static int launch_unet(hn_ctx* c, int B, cudaStream_t st, bool from_in6, bool ra
         mask &= ~(1ull << S_IN6);
         mask &= ~(1ull << (S_WF + cur));
         mask &= ~(1ull << (S_RES + cur));
-        HN_LAUNCH_PDL(c->pdl, reset_amax_kernel, dim3(1), dim3(64), 0, st, c->amax, mask);
+        HN_LAUNCH_PDL(c->pdl, reset_amax_kernel, dim3(1), dim3(64), 0, st, c->amax, mask, advance_slot);
         c->launches++;
     }
     // inc
@@ -1123,11 +1123,10 @@ static int launch_spectral(hn_ctx* c, int B, cudaStream_t st, const float* u, co
 }
 
 static int launch_iteration(hn_ctx* c, int B, cudaStream_t st) {
-    HN_TRY(launch_unet(c, B, st, false, false, true));
+    // the iteration slot (row of the residual-norm history) is advanced by the first kernel of the iteration: hn_run starts it at -1
+    HN_TRY(launch_unet(c, B, st, false, false, true, c->iter_dev));
     HN_TRY(launch_spectral(c, B, st, c->wf, c->ksq, c->src, c->src_batch, c->res, c->ssq, c->iter_dev, c->amax + S_RES + (c->cur ^ 1)));
     HN_TRY(side_join(c, st));      // the conv_state branch joins after the residual stage
-    HN_LAUNCH_PDL(c->pdl, advance_iter_kernel, dim3(1), dim3(32), 0, st, c->iter_dev);
-    c->launches++;
     return HN_OK;
 }
 
@@ -1557,7 +1556,7 @@ int hn_run(hn_ctx* c, int n_iters, float* d_rmse, float* d_wf_hist, float* d_res
         c->ssq_cap = cap;
     }
     HN_CUDA(cudaMemsetAsync(c->ssq, 0, need * sizeof(double), st));
-    HN_CUDA(cudaMemsetAsync(c->iter_dev, 0, sizeof(int), st));
+    HN_CUDA(cudaMemsetAsync(c->iter_dev, 0xFF, sizeof(int), st));      // slot -1: incremented at the start of every iteration
     const size_t total = (size_t)B * hw;
     pdl_select(c, B);
     for (int it = 0; it < n_iters; it++) {

@@ -1,7 +1,7 @@
 // layout.cuh -- boundary kernels: conversion between the reference's tensor layouts (NCHW, possibly
 // strided) and the solver's resident layouts (interleaved complex float2 / NHWC8), plus the solve setup
 // of IterativeSolver.get_initials (helmnet/hybridnet.py:522-538).  All are off the per-iteration path
-// except advance_iter_kernel (one thread) and the optional history snapshots.
+// except reset_amax_kernel (64 threads, first kernel of an iteration) and the optional history snapshots.
 #pragma once
 #include "common.cuh"
 
@@ -132,16 +132,14 @@ __global__ void finalize_rmse_kernel(const double* __restrict__ ssq, float* __re
         rmse[i] = (float)sqrt(ssq[i] * inv_count);
 }
 // zero the amax slots whose bit is set in `mask` (slots of tensors that are re-produced in this UNet pass)
-__global__ void reset_amax_kernel(unsigned* slots, unsigned long long mask) {
+// First kernel of an iteration: it also advances the iteration slot of the residual-norm history when `it` is given (the slot
+// starts at -1 in hn_run), which saves a one-thread kernel at the end of every iteration.
+__global__ void reset_amax_kernel(unsigned* slots, unsigned long long mask, int* it) {
     const int i = threadIdx.x;
     pdl_wait();
     pdl_trigger();
     if (i < 64 && ((mask >> i) & 1ull)) slots[i] = 0u;
-}
-__global__ void advance_iter_kernel(int* it) {
-    pdl_wait();
-    pdl_trigger();
-    if (threadIdx.x == 0 && blockIdx.x == 0) *it += 1;
+    if (i == 0 && it != nullptr) *it += 1;
 }
 
 }  // namespace hn

@@ -24,6 +24,20 @@ def test_laplacian_generic_radix(emu_solver):
     assert rel_l2(emu_solver.Lap(u), O.laplacian(u, O.make_operator(80, 8, 2.0, 1.0))) < 1e-6
 
 
+def test_residual_n256_per_sample_sources(emu_solver):
+    """The N = 256 residual kernels with per-sample point sources (the zero-source tile skip reads 8 column flags per tile)
+    against the oracle."""
+    from oracle import helmnet_oracle as O
+    emu_solver.set_domain_size(256, source_location=[30, 128])
+    locs = [[30, 128], [200, 5]]
+    emu_solver.set_multiple_sources(locs)
+    gen = torch.Generator().manual_seed(21)
+    wf = torch.randn(2, 2, 256, 256, generator=gen)
+    k_sq = 1.0 + torch.rand(2, 1, 256, 256, generator=gen)
+    ref = O.get_residual(wf, k_sq, O.point_sources(256, locs), O.make_operator(256, 8, 2.0, 1.0))
+    assert rel_l2(emu_solver.get_residual(wf, k_sq), ref) < 1e-6
+
+
 @pytest.mark.parametrize("pml", [8, 12, 0])
 def test_laplacian_n256_register_fft(emu_solver, pml):
     """N = 256 takes the register-resident 16 x 16 kernels (spectral256.cuh); pml 12 has threads owning two strip samples."""

@@ -27,11 +27,11 @@ def launches(path, bench_us):
             continue
         if hdr and len(r) == len(hdr):
             data.append(dict(zip(hdr, r)))
-    # the last complete iteration: from the reset_amax_kernel that opens it to the advance_iter_kernel that closes it
-    b = [i for i, d in enumerate(data) if 'advance_iter' in d['Kernel Name']][-1]
-    a = [i for i, d in enumerate(data[:b]) if 'reset_amax' in d['Kernel Name']][-1] - 1
+    # the last complete iteration: from one reset_amax_kernel (the first kernel of an iteration) to the launch before the next one
+    idx = [i for i, d in enumerate(data) if 'reset_amax' in d['Kernel Name']]
+    a, b = idx[-2] - 1, idx[-1] - 1
     out = ["# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3` (256^2 x 256, engine 2), one B200.",
-           "# One solver iteration = the launches between two advance_iter_kernel launches (replayed as one CUDA graph in production).",
+           "# One solver iteration = the launches from one reset_amax_kernel to the next (replayed as one CUDA graph in production).",
            "# Per-launch times are cold-cache and serialised by ncu: the kernel's SHARE of the iteration is what compares with bench.py.",
            f"# {'kernel':62s} {'grid':14s} {'block':12s} {'us':>8s} {'share':>6s}"]
     tot = sum(float(d['Metric Value'].replace(',', '')) / 1e3 for d in data[a + 1:b + 1])
