@@ -50,7 +50,7 @@ constexpr int PROD_WARPS = 10, EPI_WARPS = 4;
 constexpr int MMA_WARP = PROD_WARPS;
 constexpr int TMA_WARP = PROD_WARPS + 1 + EPI_WARPS;
 constexpr int THREADS = (PROD_WARPS + 1 + EPI_WARPS + 1) * 32;   // 512
-constexpr int ROWS = 32;           // output rows per strip
+constexpr int ROWS = 32;           // default output rows per strip (Args::rows is picked per launch by the host, even)
 constexpr int ST8 = 4224;          // staging bytes of one 8-channel row segment (130 px x 32 B, padded)
 constexpr int ST2 = 1152;          // staging bytes of one 2-channel row segment (132 px x 8 B starting at x0-2, padded)
 constexpr int BROW_BYTES = 1536;   // one (group, dx) B operand: 48 x 16 fp16
@@ -88,6 +88,7 @@ struct Args {
     float sigma_max;            // INC: max of the sigma profile
     float w_inv_scale;
     int H, W;
+    int rows;                    // output rows per strip (even): short strips for small batches, one per CTA slot
     int nsx, nsy, total_strips;  // strips per row / per column of one sample, and over the whole batch
 };
 
@@ -100,8 +101,8 @@ __device__ __forceinline__ Strip strip_of(int st, const Args& a) {
     const int sx = st % a.nsx, r = st / a.nsx;
     const int sy = r % a.nsy, b = r / a.nsy;
     g.x0 = sx * CW;
-    g.y0 = sy * ROWS;
-    g.R = min(ROWS, a.H - g.y0);       // even: H and ROWS are even
+    g.y0 = sy * a.rows;
+    g.R = min(a.rows, a.H - g.y0);     // even: H and rows are even
     g.NP = (g.R + 2) / 2;              // input row pairs incl. halo; input row k = 2j + t is image row y0 - 1 + k
     g.img = (size_t)b * a.H * a.W;
     return g;

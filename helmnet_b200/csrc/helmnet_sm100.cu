@@ -141,7 +141,7 @@ struct hn_ctx {
     bool pdl = false;
     int pdl_mode = 0;
     bool tcf_any_width = true; // fused DoubleConv kernels for every even width up to 256 (not only 32 / 64 / 128 / 256)
-    int tcf_min_width = 8;
+    int tcf_min_width = 6;     // (6: the bottom DoubleConv of the 96^2 training-domain size)
     int dconv_min_rows = 4;    // shortest strip of the fused DoubleConv kernels (small batches: more, shorter strips fill more SMs)
     bool fuse_bottom = true;   // decode[4] (the 8 -> 8 -> 8 DoubleConv at the bottom of the UNet) through the fused DoubleConv kernel
     // conv_state[d] (the hidden-state update) feeds nothing else in the same iteration: with side_state its kernels run on a
@@ -150,8 +150,9 @@ struct hn_ctx {
     int side_cfg = -1;
     bool side_state = false;
     bool side_pending = false;
-    int tcd_min_res = 16;      // tensor-core down-/up-sampling for output (input) widths >= this (M = 64 MMAs up to 64 pixels): every
-                               // level of the 256^2 pyramid (r1: 64, the 64- and 32-pixel levels ran on the CUDA cores, 0.18 ms)
+    int tcd_min_res = 4;       // tensor-core down-/up-sampling for output (input) widths >= this (M = 64 MMAs up to 64 pixels): every
+                               // level of the 256^2 and 96^2 pyramids (r1: 64 -- the 64- and 32-pixel levels of 256^2 ran on the CUDA
+                               // cores, 0.18 ms; 96^2 x 32: 0.290 -> 0.255 ms with the 12- and 6-pixel levels on the tensor cores too)
     Weights W;
     // residual norms
     double* ssq = nullptr;
@@ -277,11 +278,13 @@ static int build_tables(hn_ctx* c) {
     factorize(n, c->spec.radix, &c->spec.nstages);
     // lines per CTA: ~48 KB of line buffers for the row pass; the column pass needs >= 32 B segments
     int L = 2048 / n;     // ~50 KB of line buffers: four CTAs per SM
+    // small solves: half the lines per CTA, twice the CTAs (96^2 x 32: 192 CTAs with 16 lines; residual stage 0.052 -> 0.048 ms)
+    if ((long long)c->max_batch * n / 16 < 4ll * c->num_sms && L > 8) L = 8;
     if (const char* ev = getenv("HELMNET_SPEC_L")) L = atoi(ev);
     if (L < 1) L = 1;
     if (L > 16) L = 16;
     c->rows_L = L;
-    int CW = 16;
+    int CW = ((long long)c->max_batch * n / 16 < 4ll * c->num_sms) ? 8 : 16;
     if (const char* ev = getenv("HELMNET_SPEC_CW")) CW = atoi(ev);
     if (const char* ev = getenv("HELMNET_SPEC_CHUNK")) c->spec_chunk = atoi(ev);
     if (const char* ev = getenv("HELMNET_SPEC_FAST")) c->spec_fast = atoi(ev) != 0;
@@ -598,6 +601,24 @@ static inline int pdl_early(const hn_ctx* c, int total_strips, int ctas_per_sm) 
     return 0;
 }
 
+#ifdef HN_HAVE_TC
+// Output rows per strip of the per-conv row-streaming kernel (conv_tcr.cuh): 32 as in r1 while an SM has 64+ rows to do
+// (throughput-bound), otherwise whole rounds of equal strips over two CTA slots per SM; a strip of R rows streams R + 2 rows
+// (+ ~2 row steps of pipeline fill).  1024^2 x 1: the 512-pixel level ran on 64 CTAs with the fixed height.
+static int tcr_rows_per_strip(const hn_ctx* c, int H, int nsx, int B) {
+    if ((long long)B * H * nsx / c->num_sms >= 64) return H < tcr::ROWS ? H : tcr::ROWS;
+    int best = tcr::ROWS;
+    long long best_cost = -1;
+    for (int rows = 2; rows <= 128 && rows <= H; rows += 2) {
+        const long long total = (long long)nsx * ((H + rows - 1) / rows) * B;
+        const long long g = total < 2 * c->num_sms ? total : 2 * c->num_sms;
+        const long long cost = ((total + g - 1) / g) * (rows + 6);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = rows; }
+    }
+    return best;
+}
+#endif
+
 template <int SRC, int COUT, bool PRELU, int EPI>
 static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
     const size_t smem = conv3_smem_bytes(SRC, COUT);
@@ -625,7 +646,8 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
             t.error_flag = c->err_flag; t.sigma_max = 0.f; t.w_inv_scale = a.tc_inv;
             t.H = a.H; t.W = a.W;
             t.nsx = (a.W + tcr::CW - 1) / tcr::CW;
-            t.nsy = (a.H + tcr::ROWS - 1) / tcr::ROWS;
+            t.rows = tcr_rows_per_strip(c, a.H, t.nsx, B);
+            t.nsy = (a.H + t.rows - 1) / t.rows;
             t.total_strips = t.nsx * t.nsy * B;
             const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;
             t.pdl_trig = pdl_early(c, t.total_strips, 2);
@@ -650,7 +672,8 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
             t.error_flag = c->err_flag; t.sigma_max = c->pml > 0 ? (float)c->sigma_max : 0.f; t.w_inv_scale = a.tc_inv;
             t.H = a.H; t.W = a.W;
             t.nsx = (a.W + tcr::CW - 1) / tcr::CW;
-            t.nsy = (a.H + tcr::ROWS - 1) / tcr::ROWS;
+            t.rows = tcr_rows_per_strip(c, a.H, t.nsx, B);
+            t.nsy = (a.H + t.rows - 1) / t.rows;
             t.total_strips = t.nsx * t.nsy * B;
             const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;   // persistent: 2 CTAs per SM
             t.pdl_trig = pdl_early(c, t.total_strips, 2);
