@@ -492,3 +492,26 @@ def test_launch_scheduling_options_do_not_change_results(_cuda_solver_base, n, b
     monkeypatch.delenv("HELMNET_DCONV_MIN_ROWS", raising=False)
     monkeypatch.delenv("HELMNET_SIDE_STATE", raising=False)
     s._release_ctx()
+
+
+def test_large_batch_strip_paths_match_small_batch(_cuda_solver_base):
+    """The strip heights of the down / up / per-conv kernels and the launch options (PDL, side branch) are picked from the batch
+    size: a batch of 96 takes the throughput-regime choices (32-row strips, no side branch), a batch of 3 the small-solve ones.
+    The same maps must come out the same (to the block-scale noise of the tcgen05 engines, bit-identical on the fp32 engine)."""
+    from helmnet_b200.synthetic import config_sos
+    s, n = _cuda_solver_base, 256
+    maps = config_sos("C3", 3).cuda()
+    for engine, tol in ((2, 5e-6), (0, 0.0)):
+        s.set_engine(engine)
+        s.set_domain_size(n, source_location=[30, 128])
+        big = s.forward(maps.repeat(32, 1, 1, 1), num_iterations=4 if engine else 2)
+        wf_big, rm_big = big["wavefields"][0][:3].clone(), big["residual_rmse"][:, :3].clone()
+        small = s.forward(maps, num_iterations=4 if engine else 2)
+        s.sync_check()
+        if tol == 0.0:
+            assert torch.equal(small["wavefields"][0], wf_big)
+        else:
+            assert rel_l2(small["wavefields"][0], wf_big) < tol
+        assert rel_l2(small["residual_rmse"], rm_big) < 1e-5
+    s.set_engine(2)
+
