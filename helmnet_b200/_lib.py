@@ -33,6 +33,7 @@ _SIGS = {
     "hn_reset": (C.c_int, [_P, _P, C.c_int, _P]),
     "hn_set_state": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),
     "hn_run": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
+    "hn_step_backward": (C.c_int, [_P] + [_P] * 11 + [C.c_int, _P]),
     "hn_get": (C.c_int, [_P, _P, _P, _P, _P]),
     "hn_get_states": (C.c_int, [_P, _P, C.c_int, _P]),
     "hn_residual": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),

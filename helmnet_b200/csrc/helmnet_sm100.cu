@@ -24,6 +24,7 @@
 #include "spectral256.cuh"
 #include "spectral512.cuh"
 #include "spectral1024.cuh"
+#include "train.cuh"
 #ifndef HN_EMU
 #include "conv_tc.cuh"
 #include "conv_tcr.cuh"
@@ -89,6 +90,7 @@ struct Weights {
     ConvW inc[2], sig[kDepth][2], sta[kDepth][2], down[kDepth], bot[2], up[kDepth], dec[kDepth][2], outc;
 };
 
+struct TrainWs;
 struct hn_ctx {
     int device = 0, n = 0, max_batch = 0, pml = 0;
     double sigma_max = 0, k0 = 1, omega = 1;
@@ -125,6 +127,9 @@ struct hn_ctx {
     // weights
     float* wdev = nullptr;
     std::vector<float> whost;   // host copy of the packed fp32 weight blob (offsets of ConvW index both)
+    float* wraw = nullptr;      // the 48,160 parameters as loaded (state_dict order): the backward pass reads the checkpoint layouts
+    std::vector<float> wraw_host;
+    TrainWs* tws = nullptr;     // workspace of hn_step_backward, allocated on first use
     uint16_t* tcw = nullptr;   // fp16 split-weight images for the tcgen05 convolutions
     int* err_flag = nullptr;   // device watchdog flag of the tcgen05 kernels
     unsigned* amax = nullptr;  // [64] running max |x| per activation tensor (publish_amax), feeds the fp16 block scales
@@ -1153,6 +1158,8 @@ static int launch_iteration(hn_ctx* c, int B, cudaStream_t st) {
     return HN_OK;
 }
 
+#include "train_host.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // ABI
 // ------------------------------------------------------------------------------------------------
@@ -1244,6 +1251,7 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     A_(c->ssq1, B);
     A_(c->iter_dev, 4);
     A_(c->wdev, 65536);
+    A_(c->wraw, HN_NUM_WEIGHTS);
     A_(c->tcw, 458752);
     A_(c->err_flag, 4);
     A_(c->amax, 64);
@@ -1297,6 +1305,11 @@ int hn_destroy(hn_ctx* c) {
 #endif
     for (void* p : c->allocs) cudaFree(p);
     if (c->ssq) cudaFree(c->ssq);
+    if (c->tws) {
+        cudaFree(c->tws->gacc);
+        cudaFree(c->tws->base);
+        delete c->tws;
+    }
     delete c;
     return HN_OK;
 }
@@ -1354,6 +1367,8 @@ int hn_load_weights(hn_ctx* c, const float* host_blob, size_t n_floats) {
 #endif
     HN_CUDA(cudaMemcpy(c->wdev, pk.blob.data(), pk.blob.size() * 4, cudaMemcpyHostToDevice));
     c->whost = pk.blob;   // host copy: small per-layer constants are passed to the tcgen05 kernels as launch parameters
+    HN_CUDA(cudaMemcpy(c->wraw, host_blob, n_floats * sizeof(float), cudaMemcpyHostToDevice));
+    c->wraw_host.assign(host_blob, host_blob + n_floats);
     if (pk.halfs.size() > 458752) return fail(HN_ERR_STATE, "tensor-core weight images exceed the reserved buffer");
     if (!pk.halfs.empty()) HN_CUDA(cudaMemcpy(c->tcw, pk.halfs.data(), pk.halfs.size() * 2, cudaMemcpyHostToDevice));
     c->weights_set = true;
@@ -1674,6 +1689,18 @@ int hn_unet(hn_ctx* c, const float* d_in, float* d_out, int batch, void* stream)
     c->launches++;
     HN_CUDA(cudaGetLastError());
     return HN_OK;
+}
+
+int hn_step_backward(hn_ctx* c, const float* d_wf, const float* d_res, const float* d_ksq, const float* d_hflat, const float* d_g_wf,
+                     const float* d_g_res, const float* d_g_hflat, float* d_gwf_in, float* d_gres_in, float* d_ghflat_in, float* d_gparams,
+                     int batch, void* stream) {
+    DeviceGuard dev_guard(c ? c->device : -1);
+    if (!c) return fail(HN_ERR_ARG, "ctx is NULL");
+    if (batch < 1 || batch > c->max_batch) return fail(HN_ERR_ARG, "batch out of range for this context");
+    if (!c->weights_set) return fail(HN_ERR_STATE, "hn_load_weights has not been called");
+    if (!d_wf || !d_res || !d_ksq || !d_hflat || !d_gparams) return fail(HN_ERR_ARG, "NULL argument");
+    return step_backward(c, d_wf, d_res, d_ksq, d_hflat, d_g_wf, d_g_res, d_g_hflat, d_gwf_in, d_gres_in, d_ghflat_in, d_gparams, batch,
+                         (cudaStream_t)stream);
 }
 
 int hn_state_len(const hn_ctx* c) { return c ? c->state_len : HN_ERR_ARG; }

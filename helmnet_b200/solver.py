@@ -168,6 +168,53 @@ class SpectralLaplacian(nn.Module):
         return owner.apply_laplacian(x.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
 
 
+
+# --------------------------------------------------------------------------------------------------
+# training unroll: one solver step as an autograd node (reference hybridnet.py:558-623 under autograd)
+# --------------------------------------------------------------------------------------------------
+class _SingleStepFn(torch.autograd.Function):
+    """``IterativeSolver.single_step`` (hybridnet.py:558-584) as ONE node of the autograd graph.
+
+    forward: the inference kernels (hn_set_state + hn_run(1) + hn_get).  backward: ``hn_step_backward`` -- the step is
+    recomputed in fp32 with every pre-activation kept and differentiated by hand-written CUDA kernels (train.cuh): gradients
+    of the wavefield, the residual and the flattened hidden state, and of the 88 parameter tensors of ``solver.f`` (passed as
+    ``*params`` in state_dict order so that autograd routes their gradients).  k_sq and the source get no gradient, as in the
+    reference's training_step (hybridnet.py:385-410), where neither requires one.
+    """
+
+    @staticmethod
+    def forward(ctx, solver, wavefield, k_sq, residual, hflat, *params):
+        wf, ks, rs, hf = (solver._prep(t, n) for t, n in ((wavefield, "wavefield"), (k_sq, "k_sq"), (residual, "residual"), (hflat, "state")))
+        b, lib = wf.shape[0], solver.lib
+        c = solver._ensure_ctx(b)
+        lib.check(lib.hn_set_state(c, solver._ptr(wf), solver._ptr(rs), solver._ptr(ks), solver._ptr(hf), b, solver._stream()), "hn_set_state")
+        lib.check(lib.hn_run(c, 1, solver._ptr(None), solver._ptr(None), solver._ptr(None), solver._ptr(None), solver._stream()), "hn_run")
+        new_wf, new_res, new_h = torch.empty_like(wf), torch.empty_like(rs), torch.empty_like(hf)
+        lib.check(lib.hn_get(c, solver._ptr(new_wf), solver._ptr(new_res), solver._ptr(new_h), solver._stream()), "hn_get")
+        ctx.solver = solver
+        ctx.save_for_backward(wf, ks, rs, hf)
+        ctx.param_shapes = [tuple(p.shape) for p in params]
+        return new_wf, new_res, new_h
+
+    @staticmethod
+    def backward(ctx, g_wf, g_res, g_h):
+        solver = ctx.solver
+        wf, ks, rs, hf = ctx.saved_tensors
+        b, lib = wf.shape[0], solver.lib
+        c = solver._ensure_ctx(b)
+        up = [None if g is None else solver._prep(g, "gradient") for g in (g_wf, g_res, g_h)]
+        gwf_in, gres_in, gh_in = torch.empty_like(wf), torch.empty_like(rs), torch.empty_like(hf)
+        gp = torch.zeros(_lib.HN_NUM_WEIGHTS, device=wf.device)
+        ptr = solver._ptr
+        lib.check(lib.hn_step_backward(c, ptr(wf), ptr(rs), ptr(ks), ptr(hf), ptr(up[0]), ptr(up[1]), ptr(up[2]), ptr(gwf_in), ptr(gres_in),
+                                       ptr(gh_in), ptr(gp), b, solver._stream()), "hn_step_backward")
+        grads, off = [], 0
+        for shape in ctx.param_shapes:
+            cnt = int(np.prod(shape)) if len(shape) else 1
+            grads.append(gp[off: off + cnt].view(shape))
+            off += cnt
+        return (None, gwf_in, None, gres_in, gh_in, *grads)
+
 # --------------------------------------------------------------------------------------------------
 class IterativeSolver(nn.Module):
     def __init__(self, domain_size: int, k: float, omega: float, PMLsize: int, sigma_max: float, source_location: list,
@@ -539,10 +586,47 @@ class IterativeSolver(nn.Module):
             return out["wavefields"][0], out["residuals"][0]
         return out["wavefields"][0]
 
+    def _wants_grad(self, *tensors):
+        if not torch.is_grad_enabled():
+            return False
+        if any(t is not None and torch.is_tensor(t) and t.requires_grad for t in tensors):
+            return True
+        return any(p.requires_grad for p in self.f.parameters())
+
+    def _n_steps_autograd(self, wavefield, k_sq, residual, num_iterations, return_wavefields, return_states):
+        """The training unroll (reference hybridnet.py:586-623 with autograd recording): every step is one _SingleStepFn node,
+        so ``loss.backward()`` on the returned residuals / wavefields / states reaches the inputs and ``solver.f``'s parameters."""
+        params = list(self.f.parameters())
+        versions = tuple(p._version for p in params)
+        if versions != getattr(self, "_param_versions", None):     # an optimizer step mutated the parameters in place
+            self._param_versions = versions
+            self._weights_dirty = True
+        hs = self.f.get_states()
+        if any(h is None for h in hs):
+            raise ValueError("You must set or clear the state before using this module")
+        hflat = self.f.flatten_state(hs)
+        wavefields, residuals, states = [], [], []
+        for _ in range(num_iterations):
+            wavefield, residual, hflat = _SingleStepFn.apply(self, wavefield, k_sq, residual, hflat, *params)
+            self.f.set_states(hflat, flatten=True)
+            residuals.append(residual)
+            if return_wavefields:
+                wavefields.append(wavefield)
+            if return_states:
+                states.append(self.f.get_states(flatten=True))
+        if not return_wavefields:
+            wavefields.append(wavefield)
+        with torch.no_grad():
+            rmse = torch.stack([self.test_loss_function(r) for r in residuals])
+        return {"wavefields": wavefields, "residuals": residuals, "states": states, "last_iteration": num_iterations - 1,
+                "residual_rmse": rmse}
+
     def n_steps(self, wavefield, k_sq, residual, num_iterations, return_wavefields=False, return_states=False,
                 return_residuals=True):
         if num_iterations < 1:
             raise ValueError("num_iterations must be >= 1")
+        if self._wants_grad(wavefield, residual, *[h for h in self.f.get_states() if h is not None]):
+            return self._n_steps_autograd(wavefield, k_sq, residual, num_iterations, return_wavefields, return_states)
         wavefield, k_sq, residual = self._prep(wavefield, "wavefield"), self._prep(k_sq, "k_sq"), self._prep(residual, "residual")
         b = wavefield.shape[0]
         ctx = self._ensure_ctx(b)

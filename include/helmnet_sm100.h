@@ -98,6 +98,18 @@ int hn_set_state(hn_ctx* ctx, const float* d_wf, const float* d_res, const float
 int hn_run(hn_ctx* ctx, int n_iters, float* d_rmse, float* d_wf_hist, float* d_res_hist, float* d_h_hist,
            void* stream);
 
+/* Backward pass of ONE IterativeSolver.single_step (helmnet/hybridnet.py:558-584) for the training unroll
+ * IterativeSolver.n_steps under autograd (helmnet/hybridnet.py:586-623, used by training_step :385-410): what
+ * loss.backward() does through one step of the reference's graph (37 convolutions, 14 PReLUs, the 1/1e3 update and the
+ * spectral residual).  Inputs of the step as given to hn_set_state: d_wf, d_res [B,2,N,N], d_ksq [B,1,N,N], d_hflat [B,2,S].
+ * Upstream gradients of the step's outputs (any may be NULL = zero): d_g_wf, d_g_res [B,2,N,N] (new wavefield / residual),
+ * d_g_hflat [B,2,S] (new hidden states).  Results: gradients of the inputs d_gwf_in, d_gres_in [B,2,N,N], d_ghflat_in [B,2,S]
+ * (any may be NULL) and the parameter gradients ADDED to d_gparams [HN_NUM_WEIGHTS] (state_dict order, as hn_load_weights).
+ * The step is recomputed in fp32 on the CUDA cores with every pre-activation kept; k_sq and the source get no gradient. */
+int hn_step_backward(hn_ctx* ctx, const float* d_wf, const float* d_res, const float* d_ksq, const float* d_hflat,
+                     const float* d_g_wf, const float* d_g_res, const float* d_g_hflat, float* d_gwf_in, float* d_gres_in,
+                     float* d_ghflat_in, float* d_gparams, int batch, void* stream);
+
 /* Read back current wavefield / residual / flattened hidden state (NCHW); any may be NULL. */
 int hn_get(hn_ctx* ctx, float* d_wf, float* d_res, float* d_hflat, void* stream);
 

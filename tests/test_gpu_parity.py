@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import record, rel_l2
+from conftest import CKPT, record, rel_l2
 
 pytestmark = pytest.mark.gpu
 PER_ITER_TOL = 1e-5
@@ -515,3 +515,99 @@ def test_large_batch_strip_paths_match_small_batch(_cuda_solver_base):
         assert rel_l2(small["residual_rmse"], rm_big) < 1e-5
     s.set_engine(2)
 
+
+
+# ---- the training unroll, n_steps under autograd (reference hybridnet.py:586-623, 385-410) ---------------------
+@pytest.fixture(scope="module")
+def cuda_trainable():
+    from helmnet_b200 import IterativeSolver
+    s = IterativeSolver.load_from_checkpoint(CKPT, strict=False, test_data_path=None)
+    s.train()
+    s.to("cuda:0")
+    return s
+
+
+@pytest.mark.parametrize("engine,floor", [(0, 2e-5), (2, 3e-4)], ids=["fwd-simt", "fwd-tcgen05-fused"])
+@pytest.mark.parametrize("n,batch,steps", [(96, 4, 3), (256, 1, 1), (16, 3, 2)])
+def test_training_unroll_gradients(cuda_trainable, f_weights, n, batch, steps, engine, floor):
+    """loss.backward() through n_steps: gradients of all 88 parameter tensors, the wavefield, the residual and the hidden states
+    against torch.autograd through the oracle in fp64.  Bar: 3 x the distance of torch's own fp32 autograd from fp64, with a floor
+    of 2e-5 when the forward values come from the fp32 engine (the backward kernels are fp32 throughout) and 3e-4 when they come
+    from the default tcgen05 engine: the loss's cotangents are the residuals of the unrolled steps, which its 22-bit operands
+    move by up to ~5e-5 relative (measured worst gradient: 7.5e-5)."""
+    from test_emu_train import compare, run_oracle, run_ours, unroll_case
+    s = cuda_trainable
+    s.set_engine(engine)
+    s.set_domain_size(n, source_location=[n // 3, n // 2])
+    case = unroll_case(n, batch, seed=n)
+    dev_case = [[t.cuda() for t in c] if isinstance(c, list) else c.cuda() for c in case]
+    ours = run_ours(s, n, *dev_case, steps)
+    s.sync_check()
+    src = s.source.detach().cpu()
+    ref64 = run_oracle(f_weights, n, src, *case, steps, torch.float64)
+    ref32 = run_oracle(f_weights, n, src, *case, steps, torch.float32)
+    s.set_engine(2)
+    worst = compare(ours, ref64, ref32, floor=floor)
+    top = sorted(worst.items(), key=lambda kv: -kv[1][0])[:3]
+    record("training_unroll_gradients", n=n, batch=batch, steps=steps, forward_engine=engine, worst=[f"{k}: {v[0]:.2e} (torch fp32 {v[1]:.2e})" for k, v in top])
+
+
+def test_training_step_time_at_the_reference_configuration(cuda_trainable):
+    """The reference's training configuration (checkpoint hparams: 96 x 96, batch 32, unrolling_steps 10): forward + backward of
+    one training_step through this build, beside the same graph in eager PyTorch (cuDNN + cuFFT, TF32 off) on the same GPU."""
+    from oracle import helmnet_oracle as O
+    from test_emu_train import oracle_unroll, training_loss, unroll_case
+    s, n, batch, steps = cuda_trainable, 96, 32, 10
+    s.set_domain_size(n, source_location=[82, 48])
+    case = unroll_case(n, batch, seed=7)
+    wf, res, k_sq, states, cw, cs = [[t.cuda() for t in c] if isinstance(c, list) else c.cuda() for c in case]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def ours():
+        for p in s.f.parameters():
+            p.grad = None
+        s.f.set_states([h.clone() for h in states])
+        out = s.n_steps(wf, k_sq, res, steps, True, True)
+        (1e4 * torch.cat(out["residuals"]).pow(2).mean()).backward()
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    w = {k: v.detach().clone().requires_grad_(True) for k, v in s.f.state_dict().items()}
+    src = s.source.detach()
+    op_dev = None
+
+    def eager():
+        nonlocal op_dev
+        for v in w.values():
+            v.grad = None
+        # the oracle's functional step on the GPU (tables moved once)
+        if op_dev is None:
+            op_dev = {k: v.cuda() for k, v in O.make_operator(n, 8, 2.0, 1.0).items()}
+        sig = op_dev["sigmas"].unsqueeze(0)
+        u, r, st = wf, res, [h.clone() for h in states]
+        ress = []
+        for _ in range(steps):
+            d, st = O.unet_forward(w, torch.cat([u, 1e3 * r, sig.repeat(batch, 1, 1, 1)], 1), st)
+            u = d / 1e3 + u
+            r = O.get_residual(u, k_sq, src, op_dev)
+            ress.append(r)
+        (1e4 * torch.cat(ress).pow(2).mean()).backward()
+
+    times = {}
+    for name, fn in (("this_build", ours), ("eager_pytorch", eager)):
+        fn(); fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        times[name] = e0.elapsed_time(e1) / 3
+    g_ours = torch.cat([p.grad.reshape(-1) for p in s.f.parameters()])
+    g_ref = torch.cat([w[k].grad.reshape(-1) for k in s.f.state_dict().keys()])
+    err = rel_l2(g_ours, g_ref)
+    record("training_step_time", n=n, batch=batch, steps=steps, ms_this_build=times["this_build"], ms_eager_pytorch=times["eager_pytorch"],
+           grad_rel_l2_vs_eager_fp32=err)
+    print(f"training step 96^2 x 32, 10 unrolled steps: {times['this_build']:.1f} ms (eager PyTorch {times['eager_pytorch']:.1f} ms), "
+          f"parameter gradients vs eager fp32 {err:.2e}")
+    assert err < 1e-4
