@@ -208,6 +208,68 @@ def reference_throughput(n: int, batch: int, iters: int, warmup: int, threads: i
     return batch * n * n * iters / dt / 1e6, dt / iters * 1e3, "port"
 
 
+def training_step_time(dev, n=96, batch=32, steps=10, reps=3, with_reference=True):
+    """ms of forward + backward of one training step (hybridnet.py:385-417: n_steps with autograd over `steps` unrolled solver
+    steps, loss = 1e4 * mean(residuals^2), loss.backward()) through this build, and through the unmodified reference in eager
+    PyTorch on the same GPU (TF32 off).  State: the one training starts from (zero wavefield and hidden states, residual = -source)."""
+    import torch
+
+    from helmnet_b200 import IterativeSolver
+    s = IterativeSolver.load_from_checkpoint(CKPT, strict=False, test_data_path=None)
+    s.train()
+    s.to(dev)
+    s.set_domain_size(n, source_location=[82, 48])
+    sos = make_maps(n, batch).to(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def step(model):
+        for p in model.f.parameters():
+            p.grad = None
+        with torch.no_grad():
+            k_sq, wf = model.get_initials(sos)
+            model.f.clear_states(wf)
+            res = model.get_residual(wf, k_sq)
+        out = model.n_steps(wf, k_sq, res, steps, True, True)
+        loss = 1e4 * torch.cat(out["residuals"]).pow(2).mean()
+        loss.backward()
+        return loss.detach()
+
+    def timed(model):
+        step(model); step(model)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            loss = step(model)
+        e1.record()
+        torch.cuda.synchronize()
+        g = torch.cat([p.grad.reshape(-1) for p in model.f.parameters()])
+        return e0.elapsed_time(e1) / reps, float(loss), g
+
+    ms, loss, g = timed(s)
+    out = {"n": n, "batch": batch, "unrolled_steps": steps, "ms": ms, "loss": loss,
+           "definition": "get_initials + n_steps(..., 10, True, True) under autograd + loss.backward(), 48160 parameter gradients"}
+    s._release_ctx()
+    if with_reference:
+        tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            ref = load_reference_solver(n, dev)
+            if ref is not None:
+                for p in ref.f.parameters():
+                    p.requires_grad_(True)
+                ref.train()
+                ref.hparams.source_location = [82, 48]
+                with torch.no_grad():
+                    ref.set_domain_size(n, source_location=[82, 48])
+                ms_r, loss_r, g_r = timed(ref)
+                out.update(ms_eager_reference=ms_r, loss_eager_reference=loss_r, speedup=ms_r / ms,
+                           grad_rel_l2_vs_eager_reference=float((g - g_r).norm() / g_r.norm()))
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -465,6 +527,15 @@ def run_ours(args):
                 others["C2_96x96_batch32"] = quick_config(96, 32, 50)
                 others["C3_256x256_share_of_batch256_over_8gpus"] = quick_config(256, 32, 50)
 
+    # ---------------- one training step of the reference's training configuration (96 x 96, batch 32, 10 unrolled
+    # steps: n_steps under autograd + loss.backward(), hybridnet.py:385-417), beside the unmodified reference in eager PyTorch ----
+    train = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            train = training_step_time(dev, with_reference=not args.no_gpu_baseline)
+        except Exception as ex:       # an extra: never let it break the bench line
+            train = {"error": repr(ex)[-500:]}
+
     # ---------------- config[0] of BASELINE.json: the README lens (one 256x256 map), time until RMSE < 1e-3 ------------
     readme = None
     if rank == 0 and args.residual_iters > 0 and n == 256:
@@ -597,6 +668,7 @@ def run_ours(args):
             "gpu_eager_baseline": gpu_eager,
             "ms_to_residual_1e-3": ttr,
             "readme_lens_ms_to_residual_1e-3": readme,
+            "training_step": train,
             "final_rmse_max": final_rmse_max,
         }
         print(json.dumps(line))

@@ -4,7 +4,7 @@
 // SURVEY.md section 8 row f4.  hn_step_backward (train_host.cuh) recomputes the step in fp32 with every pre-activation kept,
 // then walks the UNet (helmnet/architectures.py:439-465, 240-252, 63-84) and the residual (hybridnet.py:544-584) backwards.
 // Everything here runs on the fp32 CUDA cores, one thread per pixel (data gradients) or per weight (weight gradients):
-// these kernels are the correct-first version of the row, not tuned like the inference path (DESIGN.md section 8).
+// these kernels are the correct-first version of the row, not tuned like the inference path (DESIGN.md section 7).
 //
 // Tensor layout: NHWC, contiguous, C = the real channel count (2, 6 or 8 floats per pixel) -- complex fields are float2.
 #pragma once
@@ -35,6 +35,31 @@ struct ConvArgs {
     float slope; float* act;     // act != null: act = PReLU(out) next to the pre-activation in o0 (c0 == CO)
 };
 
+// acc[co] += scale * px[ci] * ws[ci][co] over the C channels of one source pixel (C is even; 128-bit loads when C % 4 == 0:
+// a pixel of C floats is then 16-byte aligned)
+template <int CO>
+__device__ __forceinline__ void accumulate(float (&acc)[CO], const float* px, int C, float scale, const float* ws) {
+    if ((C & 3) == 0) {
+        for (int ci = 0; ci < C; ci += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(px + ci);
+            const float vv[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int co = 0; co < CO; co++) acc[co] = fmaf(vv[j], ws[(ci + j) * CO + co], acc[co]);
+        }
+    } else {
+        for (int ci = 0; ci < C; ci += 2) {
+            const float2 v = *reinterpret_cast<const float2*>(px + ci);
+            const float vv[2] = {v.x * scale, v.y * scale};
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+                for (int co = 0; co < CO; co++) acc[co] = fmaf(vv[j], ws[(ci + j) * CO + co], acc[co]);
+        }
+    }
+}
+
 template <int CO>
 __global__ void __launch_bounds__(T_THREADS) conv_kernel(ConvArgs p) {
     HN_DYN_SMEM(float, wsm);
@@ -57,16 +82,8 @@ __global__ void __launch_bounds__(T_THREADS) conv_kernel(ConvArgs p) {
                 if (xx < 0 || xx >= p.W) continue;
                 const long long q = pix + (long long)(ky - pad) * p.W + (kx - pad);
                 const float* ws = wsm + (size_t)(ky * p.ks + kx) * CI * CO;
-                for (int ci = 0; ci < p.ca; ci++) {
-                    const float v = p.a[q * p.ca + ci] * p.in_scale;
-#pragma unroll
-                    for (int co = 0; co < CO; co++) acc[co] = fmaf(v, ws[ci * CO + co], acc[co]);
-                }
-                for (int ci = 0; ci < p.cb; ci++) {
-                    const float v = p.b[q * p.cb + ci] * p.in_scale;
-#pragma unroll
-                    for (int co = 0; co < CO; co++) acc[co] = fmaf(v, ws[(p.ca + ci) * CO + co], acc[co]);
-                }
+                accumulate<CO>(acc, p.a + q * p.ca, p.ca, p.in_scale, ws);
+                if (p.cb > 0) accumulate<CO>(acc, p.b + q * p.cb, p.cb, p.in_scale, ws + p.ca * CO);
             }
         }
         const int c1 = CO - p.c0;
@@ -93,6 +110,7 @@ __global__ void __launch_bounds__(T_THREADS) conv_kernel(ConvArgs p) {
 // weight, group and CTA.
 constexpr int WG_T = 16;          // pixels per tile edge
 constexpr int WG_THREADS = 256;
+constexpr int WG_MAX_THREADS = 512;
 struct WgradArgs {
     const float* a; int ca;
     const float* b; int cb;
@@ -102,15 +120,25 @@ struct WgradArgs {
     float* gw;      // [CO][ca + cb][ks][ks]
     float* gb;      // [CO] or null
 };
+// (input pixels are stored CI + 1 floats apart: with a pitch of 2, 8 or 16 floats the nine taps of one channel would share two banks)
 __host__ __device__ inline size_t wgrad_smem_bytes(int ci, int co) {
-    return ((size_t)(WG_T + 2) * (WG_T + 2) * ci + (size_t)WG_T * WG_T * co) * sizeof(float);
+    const size_t tiles = ((size_t)(WG_T + 2) * (WG_T + 2) * (ci + 1) + (size_t)WG_T * WG_T * co) * sizeof(float);
+    const size_t red = (size_t)512 * co * sizeof(float);      // final reduction across the thread groups (WG_MAX_THREADS x CO)
+    return tiles > red ? tiles : red;
+}
+// threads per CTA: as many whole groups of (ci * k^2 + 1) threads as fit into WG_MAX_THREADS, rounded up to whole warps
+__host__ __device__ inline int wgrad_threads(int ci, int ks) {
+    const int units = ci * ks * ks + 1;
+    const int g = WG_MAX_THREADS / units > 0 ? WG_MAX_THREADS / units : 1;
+    const int t = (units * g + 31) & ~31;
+    return t > WG_MAX_THREADS ? WG_MAX_THREADS : t;
 }
 template <int CO>
-__global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(WgradArgs p) {
+__global__ void __launch_bounds__(WG_MAX_THREADS) wgrad_kernel(WgradArgs p) {
     HN_DYN_SMEM(float, sm);
-    const int CI = p.ca + p.cb, KK = p.ks * p.ks, pad = p.ks / 2, TP = WG_T + 2;
-    float* in_s = sm;                               // [TP][TP][CI], halo of one pixel
-    float* dz_s = sm + (size_t)TP * TP * CI;        // [WG_T][WG_T][CO]
+    const int CI = p.ca + p.cb, KK = p.ks * p.ks, pad = p.ks / 2, TP = WG_T + 2, PS = CI + 1;
+    float* in_s = sm;                               // [TP][TP][PS], halo of one pixel
+    float* dz_s = sm + (size_t)TP * TP * PS;        // [WG_T][WG_T][CO]
     const int tiles_x = (p.W + WG_T - 1) / WG_T, tiles_y = (p.H + WG_T - 1) / WG_T;
     const int tiles = tiles_x * tiles_y * p.B;
     const int units = CI * KK + 1;                  // the last unit is the bias (input == 1)
@@ -136,7 +164,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(WgradArgs p) {
                 const size_t g = img + (size_t)y * p.W + x;
                 v = cc < p.ca ? p.a[g * p.ca + cc] : p.b[g * p.cb + (cc - p.ca)];
             }
-            in_s[i] = v;
+            in_s[q * PS + cc] = v;
         }
         for (int i = threadIdx.x; i < WG_T * WG_T * CO; i += blockDim.x) {
             const int cc = i % CO, q = i / CO, px = q % WG_T, py = q / WG_T;
@@ -147,18 +175,25 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(WgradArgs p) {
         if (active) {
             for (int q = grp; q < WG_T * WG_T; q += groups) {
                 const int py = q / WG_T, px = q - py * WG_T;
-                const float v = is_bias ? 1.f : in_s[((py + oy) * TP + px + ox) * CI + c];
+                const float v = is_bias ? 1.f : in_s[((py + oy) * TP + px + ox) * PS + c];
 #pragma unroll
                 for (int o = 0; o < CO; o++) acc[o] = fmaf(v, dz_s[q * CO + o], acc[o]);
             }
         }
         __syncthreads();
     }
-    if (active) {
+    // the groups' partial sums meet in shared memory (the tiles are done with it): one atomicAdd per weight and CTA
+    float* red = sm;                                // [groups][units][CO]
+#pragma unroll
+    for (int o = 0; o < CO; o++) red[threadIdx.x * CO + o] = active ? acc[o] : 0.f;
+    __syncthreads();
+    if (grp == 0 && active) {
 #pragma unroll
         for (int o = 0; o < CO; o++) {
-            if (is_bias) atomicAdd(p.gb + o, acc[o]);
-            else atomicAdd(p.gw + ((size_t)o * CI + c) * KK + tap, acc[o]);
+            float tot = 0.f;
+            for (int g = 0; g < groups; g++) tot += red[(g * units + unit) * CO + o];
+            if (is_bias) atomicAdd(p.gb + o, tot);
+            else atomicAdd(p.gw + ((size_t)o * CI + c) * KK + tap, tot);
         }
     }
 }
@@ -223,12 +258,12 @@ __global__ void __launch_bounds__(T_THREADS) s2_gather_kernel(S2Args p) {
                 if (x < 0 || x >= p.Ws) continue;
                 const float* sp = p.src + ((img * p.Hs + y) * p.Ws + x) * 8;
                 const float* ws = wsm + (ky * 8 + kx) * 64;
+                const float4 v0 = *reinterpret_cast<const float4*>(sp), v1 = *reinterpret_cast<const float4*>(sp + 4);
+                const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-                for (int s = 0; s < 8; s++) {
-                    const float v = sp[s];
+                for (int s = 0; s < 8; s++)
 #pragma unroll
-                    for (int c = 0; c < 8; c++) acc[c] = fmaf(v, ws[s * 8 + c], acc[c]);
-                }
+                    for (int c = 0; c < 8; c++) acc[c] = fmaf(vv[s], ws[s * 8 + c], acc[c]);
             }
         }
         float* d = p.out + pix * 8;
@@ -257,12 +292,12 @@ __global__ void __launch_bounds__(T_THREADS) s2_scatter_kernel(S2Args p) {
                 if (x + 3 - kx < 0 || sx >= p.Ws) continue;
                 const float* sp = p.src + ((img * p.Hs + sy) * p.Ws + sx) * 8;
                 const float* ws = wsm + (ky * 8 + kx) * 64;
+                const float4 v0 = *reinterpret_cast<const float4*>(sp), v1 = *reinterpret_cast<const float4*>(sp + 4);
+                const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-                for (int s = 0; s < 8; s++) {
-                    const float v = sp[s];
+                for (int s = 0; s < 8; s++)
 #pragma unroll
-                    for (int c = 0; c < 8; c++) acc[c] = fmaf(v, ws[s * 8 + c], acc[c]);
-                }
+                    for (int c = 0; c < 8; c++) acc[c] = fmaf(vv[s], ws[s * 8 + c], acc[c]);
             }
         }
         float* d = p.out + pix * 8;

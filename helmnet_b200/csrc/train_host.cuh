@@ -134,8 +134,9 @@ static int t_wgrad(hn_ctx* c, cudaStream_t st, const float* a, int ca, const flo
     const int tiles = (r + tr::WG_T - 1) / tr::WG_T;
     const int total = tiles * tiles * B, grid = total < 2 * c->num_sms ? total : 2 * c->num_sms;
     const size_t smem = tr::wgrad_smem_bytes(p.ca + p.cb, co);
-    if (co == 8) HN_LAUNCH(tr::wgrad_kernel<8>, dim3(grid), dim3(tr::WG_THREADS), smem, st, p);
-    else if (co == 2) HN_LAUNCH(tr::wgrad_kernel<2>, dim3(grid), dim3(tr::WG_THREADS), smem, st, p);
+    const int threads = tr::wgrad_threads(p.ca + p.cb, ks);
+    if (co == 8) HN_LAUNCH(tr::wgrad_kernel<8>, dim3(grid), dim3(threads), smem, st, p);
+    else if (co == 2) HN_LAUNCH(tr::wgrad_kernel<2>, dim3(grid), dim3(threads), smem, st, p);
     else return fail(HN_ERR_ARG, "unsupported channel count in the backward pass");
     c->launches++;
     return HN_OK;

@@ -192,13 +192,18 @@ class _SingleStepFn(torch.autograd.Function):
         new_wf, new_res, new_h = torch.empty_like(wf), torch.empty_like(rs), torch.empty_like(hf)
         lib.check(lib.hn_get(c, solver._ptr(new_wf), solver._ptr(new_res), solver._ptr(new_h), solver._stream()), "hn_get")
         ctx.solver = solver
+        ctx.domain_size = int(solver.hparams.domain_size)
         ctx.save_for_backward(wf, ks, rs, hf)
         ctx.param_shapes = [tuple(p.shape) for p in params]
         return new_wf, new_res, new_h
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g_wf, g_res, g_h):
         solver = ctx.solver
+        if int(solver.hparams.domain_size) != ctx.domain_size:
+            raise RuntimeError(f"the solver's domain size changed from {ctx.domain_size} to {solver.hparams.domain_size} between "
+                               "n_steps and backward(): the step cannot be differentiated on the new operator")
         wf, ks, rs, hf = ctx.saved_tensors
         b, lib = wf.shape[0], solver.lib
         c = solver._ensure_ctx(b)
