@@ -200,14 +200,11 @@ static int launch_spectral_adjoint(hn_ctx* c, cudaStream_t st, int B, const floa
     while (L > 1 && spectral_smem_bytes(n, L, c->pml) > 200 * 1024) L >>= 1;
     const size_t smem = spectral_smem_bytes(n, L, c->pml);
 #ifndef HN_EMU
-    static size_t attr_rows = 0, attr_cols = 0;     // per-function, process-wide: keep the running maximum
-    if (smem > attr_rows) {
+    static size_t attr_smem[16] = {0};     // per function AND device; keep the running maximum (contexts of different sizes)
+    if (smem > attr_smem[c->device & 15]) {
         HN_CUDA(cudaFuncSetAttribute(tr::spectral_rows_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_rows = smem;
-    }
-    if (smem > attr_cols) {
         HN_CUDA(cudaFuncSetAttribute(tr::spectral_cols_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_cols = smem;
+        attr_smem[c->device & 15] = smem;
     }
 #endif
     const int total_rows = B * n;

@@ -132,3 +132,59 @@ def test_adjoint_of_the_spectral_operator(emu_trainable):
     lib.check(lib.hn_step_backward(ctx, s._ptr(z), s._ptr(z), s._ptr(ks32), s._ptr(hf), s._ptr(None), s._ptr(g32), s._ptr(None), s._ptr(gwf),
                                    s._ptr(None), s._ptr(None), s._ptr(gp), 1, C.c_void_p(0)), "hn_step_backward")
     assert rel_l2(gwf, u.grad) < 1e-6
+
+
+def sgd_training_steps(solver_or_weights, n, sources, cases, lr, ours):
+    """Two training_step-like updates (hybridnet.py:385-417 without the replay buffer): per-sample source maps, hidden states from
+    the 'buffer', n_steps(..., 2, True, True) under autograd, loss = 1e4 * mean(residuals^2), plain SGD on the parameters."""
+    losses = []
+    if ours:
+        s = solver_or_weights
+        opt = torch.optim.SGD(s.f.parameters(), lr=lr)
+        for wf, res, k_sq, states, _, _ in cases:
+            s.set_source_maps(sources)
+            s.f.set_states(O_flatten(states), flatten=True)
+            opt.zero_grad()
+            out = s.n_steps(wf, k_sq, res, 2, True, True)
+            loss = 1e4 * torch.cat(out["residuals"]).pow(2).mean()
+            loss.backward()
+            opt.step()                      # in-place update: the next n_steps must see the new weights
+            losses.append(float(loss.detach()))
+        return losses, {k: v.detach().clone() for k, v in s.f.state_dict().items()}
+    w = {k: v.detach().double().clone().requires_grad_(True) for k, v in solver_or_weights.items()}
+    opt = torch.optim.SGD(list(w.values()), lr=lr)
+    for wf, res, k_sq, states, _, _ in cases:
+        opt.zero_grad()
+        _, ress, _ = oracle_unroll(w, n, sources.double(), wf.double(), k_sq.double(), res.double(), [h.double() for h in states], 2)
+        loss = 1e4 * torch.cat(ress).pow(2).mean()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    return losses, {k: v.detach() for k, v in w.items()}
+
+
+def O_flatten(states):
+    from oracle import helmnet_oracle as O
+    return O.flatten_states(states)
+
+
+def test_two_sgd_steps_with_per_sample_sources_emulated(f_weights):
+    """The optimizer mutates the parameters in place between two unrolls: the second one must run (forward AND backward) on the
+    updated weights, with one source map per sample as training_step sets them (hybridnet.py:398-399)."""
+    from emu_backend import EmuLib
+    from helmnet_b200 import IterativeSolver
+    from oracle import helmnet_oracle as O
+    n, batch, lr = 16, 2, 1e-6
+    s = IterativeSolver.load_from_checkpoint(CKPT, strict=False, test_data_path=None, _backend=EmuLib())
+    s.train()
+    s.set_domain_size(n, source_location=[5, 8])
+    sources = O.point_sources(n, [[5, 8], [11, 3]]).contiguous()
+    cases = [unroll_case(n, batch, seed=31), unroll_case(n, batch, seed=32)]
+    l_ours, w_ours = sgd_training_steps(s, n, sources, cases, lr, ours=True)
+    l_ref, w_ref = sgd_training_steps(f_weights, n, sources, cases, lr, ours=False)
+    assert max(abs(a - b) / abs(b) for a, b in zip(l_ours, l_ref)) < 1e-5
+    moved = max(rel_l2(w_ref[k], f_weights[k]) for k in w_ref)
+    assert moved > 1e-4                                                  # the update is not a no-op
+    for k in w_ref:                                                      # the UPDATE itself agrees to 1e-4
+        d_ours, d_ref = w_ours[k].double() - f_weights[k].double(), w_ref[k] - f_weights[k].double()
+        assert float((d_ours - d_ref).norm()) <= 1e-4 * float(d_ref.norm()) + 1e-7 * float(f_weights[k].double().norm()), k

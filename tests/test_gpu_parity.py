@@ -552,6 +552,34 @@ def test_training_unroll_gradients(cuda_trainable, f_weights, n, batch, steps, e
     record("training_unroll_gradients", n=n, batch=batch, steps=steps, forward_engine=engine, worst=[f"{k}: {v[0]:.2e} (torch fp32 {v[1]:.2e})" for k, v in top])
 
 
+def test_two_sgd_steps_with_per_sample_sources(f_weights):
+    """training_step without the replay buffer, twice: per-sample source maps (hybridnet.py:398-399), hidden states handed in,
+    n_steps under autograd, backward, an in-place SGD update -- the second unroll must run forward and backward on the updated
+    weights.  Checked against the same two updates through torch.autograd on the oracle in fp64."""
+    from helmnet_b200 import IterativeSolver
+    from oracle import helmnet_oracle as O
+    from test_emu_train import sgd_training_steps, unroll_case
+    n, batch, lr = 96, 4, 1e-6
+    s = IterativeSolver.load_from_checkpoint(CKPT, strict=False, test_data_path=None)
+    s.train()
+    s.to("cuda:0")
+    s.set_domain_size(n, source_location=[82, 48])
+    sources = O.point_sources(n, [[82, 48], [20, 30], [50, 50], [70, 9]]).contiguous()
+    cases = [unroll_case(n, batch, seed=31), unroll_case(n, batch, seed=32)]
+    dev_cases = [[[t.cuda() for t in c] if isinstance(c, list) else c.cuda() for c in case] for case in cases]
+    l_ours, w_ours = sgd_training_steps(s, n, sources.cuda(), dev_cases, lr, ours=True)
+    s.sync_check()
+    l_ref, w_ref = sgd_training_steps(f_weights, n, sources, cases, lr, ours=False)
+    e_loss = max(abs(a - b) / abs(b) for a, b in zip(l_ours, l_ref))
+    worst = 0.0
+    for k in w_ref:
+        base = f_weights[k].double()
+        d_ours, d_ref = w_ours[k].double().cpu() - base, w_ref[k] - base
+        worst = max(worst, float((d_ours - d_ref).norm()) / (float(d_ref.norm()) + 1e-3 * float(base.norm())))
+    record("two_sgd_steps", n=n, batch=batch, loss_rel_err=e_loss, worst_update_err=worst)
+    assert e_loss < 1e-4 and worst < 3e-4
+
+
 def test_training_step_time_at_the_reference_configuration(cuda_trainable):
     """The reference's training configuration (checkpoint hparams: 96 x 96, batch 32, unrolling_steps 10): forward + backward of
     one training_step through this build, beside the same graph in eager PyTorch (cuDNN + cuFFT, TF32 off) on the same GPU."""
