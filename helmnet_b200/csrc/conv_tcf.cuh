@@ -117,7 +117,41 @@ struct Args {
     int rows;                   // output rows per strip (even)
     int spi;                    // strips per image
     int total_strips;
+    int bal;                    // != 0: balanced strips (strip_of): the batch size; the grid then is one chunk of rows per CTA
 };
+
+// Strip i of this CTA (image b, first output row y0, R rows); false when it has none.
+//   bal == 0: strips of `rows` rows, strip st = blockIdx.x + i * gridDim.x of the batch (whole rounds of equal strips).
+//   bal != 0: the rows of all images are laid end to end, each image preceded by BAL_PAD virtual rows that stand for the cost of
+//             starting a strip (4 recomputed halo rows + pipeline fill), and CTA c takes the c-th of gridDim.x equal chunks of that
+//             line: every CTA gets the same rows + BAL_PAD * strips, whatever the ratio of images to SMs (one image boundary inside a
+//             chunk costs that CTA BAL_PAD rows of work less).  All boundaries are even.
+constexpr int BAL_PAD = 8;
+__device__ __forceinline__ bool strip_of(const Args& a, int i, int& b, int& y0, int& R) {
+    if (a.bal == 0) {
+        const int st = (int)blockIdx.x + i * (int)gridDim.x;
+        if (st >= a.total_strips) return false;
+        b = st / a.spi;
+        y0 = (st - b * a.spi) * a.rows;
+        R = min(a.rows, a.H - y0);
+        return true;
+    }
+    const int HV = a.H + BAL_PAD;
+    const long long VT = (long long)a.bal * HV;
+    const int v0 = (int)((VT * blockIdx.x / gridDim.x) & ~1ll);
+    const int v1 = (blockIdx.x + 1 == gridDim.x) ? (int)VT : (int)((VT * (blockIdx.x + 1) / gridDim.x) & ~1ll);
+    int found = -1;
+    for (int bb = v0 / HV; bb * HV < v1; bb++) {
+        const int ys = max(0, v0 - bb * HV - BAL_PAD), ye = min(a.H, v1 - bb * HV - BAL_PAD);
+        if (ye > ys && ++found == i) {
+            b = bb;
+            y0 = ys;
+            R = ye - ys;
+            return true;
+        }
+    }
+    return false;
+}
 
 using tcr::mbar_arrive;
 using tcr::mbar_arrive_expect_tx;
@@ -343,16 +377,14 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
     const float mult2 = __uint_as_float((uint32_t)(267 - e_mid) << 23);
     const float scale2 = __uint_as_float((uint32_t)(e_mid - 13) << 23) * a.w_inv2;
 
-    const int rows = a.rows, spi = a.spi;
     bool ok = true;
     if (warp == TMA_WARP) {
         // =============================== TMA issuer ===============================================================
         if (lane == 0) {
             int gj = 0;
 #pragma unroll 1
-            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-                const int b = st / spi, y0 = (st - b * spi) * rows;
-                const int R = min(rows, H - y0), NP1 = (R + 4) / 2;
+            for (int si = 0, b, y0, R; ok && strip_of(a, si, b, y0, R); si++) {
+                const int NP1 = (R + 4) / 2;
                 const size_t img = (size_t)b * H * Wa;
                 const uint32_t row_tx = (uint32_t)Wa * (uint32_t)(SROW / W);   // bytes one image row brings in
 #pragma unroll 1
@@ -396,9 +428,8 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
         const int sw16 = ((x >> 2) & 1) * 16;
         int gj = 0;
 #pragma unroll 1
-        for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-            const int b = st / spi, y0 = (st - b * spi) * rows;
-            const int R = min(rows, H - y0), NP1 = (R + 4) / 2;
+        for (int si = 0, b, y0, R; ok && strip_of(a, si, b, y0, R); si++) {
+            const int NP1 = (R + 4) / 2;
 #pragma unroll 1
             for (int j = 0; j < NP1; j++, gj++) {
                 const int sidx = gj % NSP, s = gj % SRP1;
@@ -471,9 +502,8 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
             constexpr uint32_t kRow16 = (uint32_t)(A1ROW >> 4);
             int gj = 0, gmp = 0;   // global input pair / mid pair counters at the start of the strip
 #pragma unroll 1
-            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-                const int b = st / spi, y0 = (st - b * spi) * rows;
-                const int R = min(rows, H - y0), NP1 = (R + 4) / 2, RM = R + 2;
+            for (int si = 0, b, y0, R; ok && strip_of(a, si, b, y0, R); si++) {
+                const int NP1 = (R + 4) / 2, RM = R + 2;
 #pragma unroll 1
                 for (int j = 0; j < NP1; j++) {
                     const int g_ = gj + j, s = g_ % SRP1;
@@ -506,9 +536,8 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
             constexpr uint32_t kRow16 = (uint32_t)(A2ROW >> 4);
             int gmp = 0, gop = 0;
 #pragma unroll 1
-            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-                const int b = st / spi, y0 = (st - b * spi) * rows;
-                const int R = min(rows, H - y0), NM = (R + 2) / 2;
+            for (int si = 0, b, y0, R; ok && strip_of(a, si, b, y0, R); si++) {
+                const int NM = (R + 2) / 2;
 #pragma unroll 1
                 for (int p = 0; p < NM; p++) {
                     const int g_ = gmp + p, s = g_ % SRP2;
@@ -539,9 +568,8 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + ACC1 + (uint32_t)(half * TR * NC);
         int gj = 0, gmp = 0;
 #pragma unroll 1
-        for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-            const int b = st / spi, y0 = (st - b * spi) * rows;
-            const int R = min(rows, H - y0), NP1 = (R + 4) / 2, NM = (R + 2) / 2;
+        for (int si = 0, b, y0, R; ok && strip_of(a, si, b, y0, R); si++) {
+            const int NP1 = (R + 4) / 2, NM = (R + 2) / 2;
 #pragma unroll 1
             for (int p = 0; p < NM; p++) {
                 const int gjd = gj + p + 1;                 // input pair that completes mid rows 2p, 2p+1
@@ -592,9 +620,8 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
         float lmax = 0.f;
         int gmp = 0, gop = 0;
 #pragma unroll 1
-        for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-            const int b = st / spi, y0 = (st - b * spi) * rows;
-            const int R = min(rows, H - y0), NM = (R + 2) / 2;
+        for (int si = 0, b, y0, R; ok && strip_of(a, si, b, y0, R); si++) {
+            const int NM = (R + 2) / 2;
             const size_t img = (size_t)b * H * Wa;
 #pragma unroll 1
             for (int q = 0; q < R / 2; q++) {

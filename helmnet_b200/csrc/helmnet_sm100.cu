@@ -148,6 +148,7 @@ struct hn_ctx {
     bool tcf_any_width = true; // fused DoubleConv kernels for every even width up to 256 (not only 32 / 64 / 128 / 256)
     int tcf_min_width = 6;     // (6: the bottom DoubleConv of the 96^2 training-domain size)
     int dconv_min_rows = 4;    // shortest strip of the fused DoubleConv kernels (small batches: more, shorter strips fill more SMs)
+    bool dconv_balance = true; // balanced strips of the fused DoubleConv kernels where the model predicts a gain (HELMNET_DCONV_BALANCE=0: off)
     bool fuse_bottom = true;   // decode[4] (the 8 -> 8 -> 8 DoubleConv at the bottom of the UNet) through the fused DoubleConv kernel
     // conv_state[d] (the hidden-state update) feeds nothing else in the same iteration: with side_state its kernels run on a
     // second stream / graph branch that forks after conv_signal[d] and joins at the end of the iteration, off the critical path
@@ -916,8 +917,21 @@ static int launch_dconv_nh(hn_ctx* c, const tcf::Args& t0, int B, cudaStream_t s
     t.rows = dconv_rows_per_strip(t.H, B, cap, c->dconv_min_rows);
     t.spi = (t.H + t.rows - 1) / t.rows;
     t.total_strips = t.spi * B;
-    const int grid = t.total_strips < cap ? t.total_strips : cap;
+    int grid = t.total_strips < cap ? t.total_strips : cap;
     t.pdl_trig = pdl_early(c, t.total_strips, NH == 2 ? 1 : 2);
+    // Balanced strips (conv_tcf.cuh: strip_of): one chunk of the images' rows laid end to end per CTA slot instead of whole rounds
+    // of equal strips -- when the number of images is no multiple of the SMs (256^2 x 32: 128 strips of 64 rows on 148 SMs, 71 row
+    // steps each; balanced: 148 chunks of ~57 steps).  Taken when the model (rows + 7 per strip, as above) predicts a gain of 3 %.
+    if (c->dconv_balance) {
+        const long long uniform = (long long)((t.total_strips + grid - 1) / grid) * (t.rows + 7);
+        const long long vt = (long long)B * (t.H + tcf::BAL_PAD);
+        const long long balanced = (vt + cap - 1) / cap + tcf::BAL_PAD + 2;      // chunk + one strip start + even rounding
+        if (vt / cap >= 12 && balanced * 100 <= uniform * 97) {
+            t.bal = B;
+            grid = cap;
+            t.pdl_trig = c->pdl_mode == 1 || c->pdl_mode == 2;     // equal work per CTA: placement does not matter
+        }
+    }
     HN_LAUNCH_PDL(c->pdl, (tcf::dconv_tcf_kernel<SRC, NH, EPI>), dim3(grid), dim3(tcf::threads(NH)), tcf::smem_bytes(SRC, NH), st, t);
     c->launches++;
     return 1;
@@ -1265,6 +1279,7 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     if (const char* pv = getenv("HELMNET_SRC_SKIP")) c->src_skip = atoi(pv) != 0;
     if (const char* pv = getenv("HELMNET_FUSE_BOTTOM")) c->fuse_bottom = atoi(pv) != 0;
     if (const char* pv = getenv("HELMNET_SIDE_STATE")) c->side_cfg = atoi(pv);
+    if (const char* pv = getenv("HELMNET_DCONV_BALANCE")) c->dconv_balance = atoi(pv) != 0;
 #ifndef HN_EMU
     if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail(HN_ERR_CUDA, "cudaStreamCreate failed"));
     for (int d = 0; d < kDepth; d++)
