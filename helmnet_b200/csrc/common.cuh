@@ -104,6 +104,29 @@ __device__ __forceinline__ unsigned ld_fresh(const unsigned* p) {
 #endif
 }
 
+// Balanced strips of the persistent row-streaming kernels (conv_tcf / conv_tcr_down / conv_tcr_up).  The rows of all `batch`
+// images (H rows each) are laid end to end, each image preceded by `pad` virtual rows that stand for the cost of starting a strip
+// (recomputed halo rows + pipeline fill), and CTA c takes the c-th of gridDim.x equal chunks of that line: every CTA carries the
+// same rows + pad * strips whatever the ratio of images to CTA slots (a chunk that crosses an image boundary gets `pad` rows of
+// work less).  Returns strip i of this CTA (image b, first row y0, R rows; all even when H and pad are) or false when it has none.
+__device__ __forceinline__ bool balanced_strip(int batch, int H, int pad, int i, int& b, int& y0, int& R) {
+    const int HV = H + pad;
+    const long long VT = (long long)batch * HV;
+    const int v0 = (int)((VT * blockIdx.x / gridDim.x) & ~1ll);
+    const int v1 = (blockIdx.x + 1 == gridDim.x) ? (int)VT : (int)((VT * (blockIdx.x + 1) / gridDim.x) & ~1ll);
+    int found = -1;
+    for (int bb = v0 / HV; bb * HV < v1; bb++) {
+        const int ys = max(0, v0 - bb * HV - pad), ye = min(H, v1 - bb * HV - pad);
+        if (ye > ys && ++found == i) {
+            b = bb;
+            y0 = ys;
+            R = ye - ys;
+            return true;
+        }
+    }
+    return false;
+}
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.y * b.x + a.x * b.y);
 }

@@ -136,21 +136,7 @@ __device__ __forceinline__ bool strip_of(const Args& a, int i, int& b, int& y0, 
         R = min(a.rows, a.H - y0);
         return true;
     }
-    const int HV = a.H + BAL_PAD;
-    const long long VT = (long long)a.bal * HV;
-    const int v0 = (int)((VT * blockIdx.x / gridDim.x) & ~1ll);
-    const int v1 = (blockIdx.x + 1 == gridDim.x) ? (int)VT : (int)((VT * (blockIdx.x + 1) / gridDim.x) & ~1ll);
-    int found = -1;
-    for (int bb = v0 / HV; bb * HV < v1; bb++) {
-        const int ys = max(0, v0 - bb * HV - BAL_PAD), ye = min(a.H, v1 - bb * HV - BAL_PAD);
-        if (ye > ys && ++found == i) {
-            b = bb;
-            y0 = ys;
-            R = ye - ys;
-            return true;
-        }
-    }
-    return false;
+    return balanced_strip(a.bal, a.H, BAL_PAD, i, b, y0, R);
 }
 
 using tcr::mbar_arrive;

@@ -61,6 +61,7 @@ struct Args {
     int H, W;                   // input resolution
     int rows_o;                 // output rows per strip: small batches take short strips so that every SM gets one
     int nsx, nsy, total_strips;
+    int bal;                    // != 0 (nsx == 1 only): balanced strips over the output rows of `bal` images (common.cuh: balanced_strip)
 };
 
 struct Strip {
@@ -78,6 +79,25 @@ __device__ __forceinline__ Strip strip_of(int st, const Args& a) {
     g.img_in = (size_t)b * a.H * a.W;
     g.img_out = (size_t)b * (a.H >> 1) * (a.W >> 1);
     return g;
+}
+constexpr int BAL_PAD = 6;     // a strip start costs ~5 row steps (3 extra input row pairs + fill)
+// strip i of this CTA; false when it has none
+__device__ __forceinline__ bool strip_at(const Args& a, int i, Strip& g) {
+    if (a.bal == 0) {
+        const int st = (int)blockIdx.x + i * (int)gridDim.x;
+        if (st >= a.total_strips) return false;
+        g = strip_of(st, a);
+        return true;
+    }
+    int b, oy0, Ro;
+    if (!balanced_strip(a.bal, a.H >> 1, BAL_PAD, i, b, oy0, Ro)) return false;
+    g.ox0 = 0;
+    g.oy0 = oy0;
+    g.Ro = Ro;
+    g.NP = Ro + 3;
+    g.img_in = (size_t)b * a.H * a.W;
+    g.img_out = (size_t)b * (a.H >> 1) * (a.W >> 1);
+    return true;
 }
 
 __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
@@ -158,8 +178,9 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
         if (lane == 0) {
             int gj = 0;
 #pragma unroll 1
-            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-                const Strip g = strip_of(st, a);
+            for (int si = 0; ok; si++) {
+                Strip g;
+                if (!strip_at(a, si, g)) break;
                 const int xb = 2 * g.ox0 - 4;                               // first staged pixel (even)
                 const int lo = max(0, xb), hi = min(W, xb + 2 * PS - 8);    // 264 pixels cover every tap of 128 outputs
                 const uint32_t rb = (uint32_t)(hi - lo) * 32u;
@@ -193,8 +214,9 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
         if (p < PS) {
             int gj = 0;
 #pragma unroll 1
-            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-                const Strip g = strip_of(st, a);
+            for (int si = 0; ok; si++) {
+                Strip g;
+                if (!strip_at(a, si, g)) break;
                 const int xb = 2 * g.ox0 - 4;
                 const int gxe = xb + 2 * p, gxo = gxe + 1;
                 const bool oke = (p < PS - 4) && gxe >= 0 && gxe < W, oko = (p < PS - 4) && gxo >= 0 && gxo < W;
@@ -250,8 +272,9 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
             const uint32_t kIdesc64 = kIdescBase | (8u << 17);
             int gj = 0, go = 0;
 #pragma unroll 1
-            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-                const Strip gs = strip_of(st, a);
+            for (int si = 0; ok; si++) {
+                Strip gs;
+                if (!strip_at(a, si, gs)) break;
                 const int Ro = gs.Ro;
 #pragma unroll 1
                 for (int j = 0; j < gs.NP; j++, gj++) {
@@ -294,8 +317,9 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
         float lmax = 0.f;
         int gj = 0, go = 0;
 #pragma unroll 1
-        for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-            const Strip gs = strip_of(st, a);
+        for (int si = 0; ok; si++) {
+            Strip gs;
+            if (!strip_at(a, si, gs)) break;
             const int ox = m64 ? (lane < 16 ? gs.ox0 + quad * 16 + lane : Wo) : gs.ox0 + quad * 32 + lane;
 #pragma unroll 1
             for (int oyl = 0; oyl < gs.Ro; oyl++) {

@@ -57,6 +57,7 @@ struct Args {
     int Hi, Wi;
     int nsx, nsy, total_strips;
     int rows_i;                 // input rows per strip (even)
+    int bal;                    // != 0 (nsx == 1 only): balanced strips over the input rows of `bal` images (common.cuh: balanced_strip)
 };
 
 struct Strip {
@@ -74,6 +75,25 @@ __device__ __forceinline__ Strip strip_of(int st, const Args& a) {
     g.img_in = (size_t)b * a.Hi * a.Wi;
     g.img_out = g.img_in * 4;
     return g;
+}
+constexpr int BAL_PAD = 6;     // a strip start costs ~6 row steps (4 extra input rows + fill)
+// strip i of this CTA; false when it has none
+__device__ __forceinline__ bool strip_at(const Args& a, int i, Strip& g) {
+    if (a.bal == 0) {
+        const int st = (int)blockIdx.x + i * (int)gridDim.x;
+        if (st >= a.total_strips) return false;
+        g = strip_of(st, a);
+        return true;
+    }
+    int b, iy0, Ri;
+    if (!balanced_strip(a.bal, a.Hi, BAL_PAD, i, b, iy0, Ri)) return false;
+    g.x0 = 0;
+    g.iy0 = iy0;
+    g.Ri = Ri;
+    g.NP = (Ri + 4) / 2;
+    g.img_in = (size_t)b * a.Hi * a.Wi;
+    g.img_out = g.img_in * 4;
+    return true;
 }
 
 __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
@@ -149,8 +169,9 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
         if (lane == 0) {
             int gj = 0;
 #pragma unroll 1
-            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-                const Strip g = strip_of(st, a);
+            for (int si = 0; ok; si++) {
+                Strip g;
+                if (!strip_at(a, si, g)) break;
                 const int lo = max(0, g.x0 - 2), hi = min(Wi, g.x0 + CW + 2);
                 const uint32_t rb = (uint32_t)(hi - lo) * 32u;
 #pragma unroll 1
@@ -181,8 +202,9 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
         if (p < PS) {
             int gj = 0;
 #pragma unroll 1
-            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-                const Strip g = strip_of(st, a);
+            for (int si = 0; ok; si++) {
+                Strip g;
+                if (!strip_at(a, si, g)) break;
                 const int gx = g.x0 - 2 + p;
                 const bool colok = (p < CW + 4) && gx >= 0 && gx < Wi;
 #pragma unroll 1
@@ -224,8 +246,9 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
             constexpr uint32_t kRow16 = ROW_OP_BYTES >> 4;
             int gj = 0, go = 0;   // go: output rows finished in previous strips (multiple of 4)
 #pragma unroll 1
-            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-                const Strip gs = strip_of(st, a);
+            for (int si = 0; ok; si++) {
+                Strip gs;
+                if (!strip_at(a, si, gs)) break;
                 const int Ro = 2 * gs.Ri;
 #pragma unroll 1
                 for (int j = 0; j < gs.NP; j++, gj++) {
@@ -268,8 +291,9 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
         float lmax = 0.f;
         int gj = 0, go = 0;
 #pragma unroll 1
-        for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-            const Strip gs = strip_of(st, a);
+        for (int si = 0; ok; si++) {
+            Strip gs;
+            if (!strip_at(a, si, gs)) break;
             const int cell = m64 ? (lane < 16 ? gs.x0 + quad * 16 + lane : Wi) : gs.x0 + quad * 32 + lane;
             const int Ro = 2 * gs.Ri;
 #pragma unroll 1

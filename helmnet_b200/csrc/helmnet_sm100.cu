@@ -148,7 +148,8 @@ struct hn_ctx {
     bool tcf_any_width = true; // fused DoubleConv kernels for every even width up to 256 (not only 32 / 64 / 128 / 256)
     int tcf_min_width = 6;     // (6: the bottom DoubleConv of the 96^2 training-domain size)
     int dconv_min_rows = 4;    // shortest strip of the fused DoubleConv kernels (small batches: more, shorter strips fill more SMs)
-    bool dconv_balance = true; // balanced strips of the fused DoubleConv kernels where the model predicts a gain (HELMNET_DCONV_BALANCE=0: off)
+    int dconv_balance = 2;     // balanced strips where the model predicts a gain (HELMNET_DCONV_BALANCE: 0 off, 1 the fused DoubleConv
+                               // kernels only, 2 also the down- / up-sampling kernels)
     bool fuse_bottom = true;   // decode[4] (the 8 -> 8 -> 8 DoubleConv at the bottom of the UNet) through the fused DoubleConv kernel
     // conv_state[d] (the hidden-state update) feeds nothing else in the same iteration: with side_state its kernels run on a
     // second stream / graph branch that forks after conv_signal[d] and joins at the end of the iteration, off the critical path
@@ -814,8 +815,22 @@ static int launch_down(hn_ctx* c, int d, int B, cudaStream_t st) {
         }
         t.nsy = (r / 2 + t.rows_o - 1) / t.rows_o;
         t.total_strips = t.nsx * t.nsy * B;
-        const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;
+        int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;
         t.pdl_trig = pdl_early(c, t.total_strips, 2);
+        t.bal = 0;
+        if (c->dconv_balance >= 2 && t.nsx == 1) {     // balanced strips (common.cuh: balanced_strip) where the model predicts 3 %
+            const int cap = 2 * c->num_sms;
+            const long long uniform = (long long)((t.total_strips + tgrid - 1) / tgrid) * (t.rows_o + 5);
+            const long long vt = (long long)B * (r / 2 + tcd::BAL_PAD);
+            const long long balanced = (vt + cap - 1) / cap + tcd::BAL_PAD + 2;
+            // (uniform 32-row strips at 64+ rows per SM pair a long and a short strip list per SM: compare per SM, not per slot)
+            const long long uniform_sm = (long long)B * (r / 2) / c->num_sms >= 64 ? ((long long)t.total_strips * (t.rows_o + 5) + c->num_sms - 1) / c->num_sms : 2 * uniform;
+            if (vt / cap >= 12 && 2 * balanced * 100 <= uniform_sm * 97) {
+                t.bal = B;
+                tgrid = cap;
+                t.pdl_trig = c->pdl_mode == 1 || c->pdl_mode == 2;
+            }
+        }
         HN_LAUNCH_PDL(c->pdl, (tcd::down_tcr_kernel), dim3(tgrid), dim3(tcr::THREADS), tcd::SMEM_BYTES, st, t);
         c->launches++;
         return HN_OK;
@@ -874,8 +889,19 @@ static int launch_up(hn_ctx* c, int d, int B, cudaStream_t st) {
         }
         t.nsy = (t.Hi + t.rows_i - 1) / t.rows_i;
         t.total_strips = t.nsx * t.nsy * B;
-        const int tgrid = t.total_strips < c->num_sms ? t.total_strips : c->num_sms;   // one CTA per SM (owns all 512 TMEM columns)
+        int tgrid = t.total_strips < c->num_sms ? t.total_strips : c->num_sms;   // one CTA per SM (owns all 512 TMEM columns)
         t.pdl_trig = pdl_early(c, t.total_strips, 1);
+        t.bal = 0;
+        if (c->dconv_balance >= 2 && t.nsx == 1) {     // balanced strips (common.cuh: balanced_strip) where the model predicts 3 %
+            const int cap = c->num_sms;
+            const long long uniform = (long long)((t.total_strips + tgrid - 1) / tgrid) * (t.rows_i + 6);
+            const long long vt = (long long)B * (t.Hi + tcu::BAL_PAD);
+            const long long balanced = (vt + cap - 1) / cap + tcu::BAL_PAD + 2;
+            if (vt / cap >= 12 && balanced * 100 <= uniform * 97) {
+                t.bal = B;
+                tgrid = cap;
+            }
+        }
         HN_LAUNCH_PDL(c->pdl, (tcu::up_tcr_kernel), dim3(tgrid), dim3(tcr::THREADS), tcu::SMEM_BYTES, st, t);
         c->launches++;
     } else
@@ -1279,7 +1305,7 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     if (const char* pv = getenv("HELMNET_SRC_SKIP")) c->src_skip = atoi(pv) != 0;
     if (const char* pv = getenv("HELMNET_FUSE_BOTTOM")) c->fuse_bottom = atoi(pv) != 0;
     if (const char* pv = getenv("HELMNET_SIDE_STATE")) c->side_cfg = atoi(pv);
-    if (const char* pv = getenv("HELMNET_DCONV_BALANCE")) c->dconv_balance = atoi(pv) != 0;
+    if (const char* pv = getenv("HELMNET_DCONV_BALANCE")) c->dconv_balance = atoi(pv);
 #ifndef HN_EMU
     if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail(HN_ERR_CUDA, "cudaStreamCreate failed"));
     for (int d = 0; d < kDepth; d++)
