@@ -494,6 +494,30 @@ def test_launch_scheduling_options_do_not_change_results(_cuda_solver_base, n, b
     s._release_ctx()
 
 
+@pytest.mark.parametrize("n,b", [(256, 40), (128, 100)])
+def test_balanced_strips_are_bit_identical(_cuda_solver_base, n, b, monkeypatch):
+    """Balanced strips (common.cuh: balanced_strip; chunks that start and end anywhere inside an image, several images per CTA) against
+    whole rounds of equal strips: the same rows are computed with the same accumulation order, so the wavefields must be
+    bit-identical (the batch sizes are no multiple of the SM count, so chunks cross image boundaries at every offset)."""
+    s = _cuda_solver_base
+    s.set_engine(2)
+    g = torch.Generator().manual_seed(n + b)
+    sos = (1.0 + torch.rand(b, 1, n, n, generator=g)).cuda()
+    outs = []
+    for mode in ("0", "2"):
+        monkeypatch.setenv("HELMNET_DCONV_BALANCE", mode)
+        s._release_ctx()
+        s.set_domain_size(n, source_location=[n // 8, n // 2])
+        out = s.forward(sos, num_iterations=3)
+        s.sync_check()
+        outs.append((out["wavefields"][0].clone(), out["residual_rmse"].clone()))
+    monkeypatch.delenv("HELMNET_DCONV_BALANCE", raising=False)
+    s._release_ctx()
+    assert torch.isfinite(outs[0][0]).all()
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert rel_l2(outs[1][1], outs[0][1]) < 1e-6
+
+
 def test_large_batch_strip_paths_match_small_batch(_cuda_solver_base):
     """The strip heights of the down / up / per-conv kernels and the launch options (PDL, side branch) are picked from the batch
     size: a batch of 96 takes the throughput-regime choices (32-row strips, no side branch), a batch of 3 the small-solve ones.
