@@ -90,6 +90,7 @@ struct Args {
     int H, W;
     int rows;                    // output rows per strip (even): short strips for small batches, one per CTA slot
     int nsx, nsy, total_strips;  // strips per row / per column of one sample, and over the whole batch
+    int bal;                     // != 0: balanced strips (common.cuh: balanced_strip) over the rows of bal = batch * nsx column strips
 };
 
 struct Strip {
@@ -106,6 +107,25 @@ __device__ __forceinline__ Strip strip_of(int st, const Args& a) {
     g.NP = (g.R + 2) / 2;              // input row pairs incl. halo; input row k = 2j + t is image row y0 - 1 + k
     g.img = (size_t)b * a.H * a.W;
     return g;
+}
+constexpr int BAL_PAD = 6;     // a strip start costs ~6 row steps (2 halo rows + pipeline fill)
+// strip i of this CTA; false when it has none
+__device__ __forceinline__ bool strip_at(const Args& a, int i, Strip& g) {
+    if (a.bal == 0) {
+        const int st = (int)blockIdx.x + i * (int)gridDim.x;
+        if (st >= a.total_strips) return false;
+        g = strip_of(st, a);
+        return true;
+    }
+    int bi, y0, R;
+    if (!balanced_strip(a.bal, a.H, BAL_PAD, i, bi, y0, R)) return false;
+    const int b = bi / a.nsx, sx = bi - b * a.nsx;
+    g.x0 = sx * CW;
+    g.y0 = y0;
+    g.R = R;
+    g.NP = (R + 2) / 2;
+    g.img = (size_t)b * a.H * a.W;
+    return true;
 }
 
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -250,8 +270,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
         if (lane == 0) {
             int gj = 0;
 #pragma unroll 1
-            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-                const Strip g = strip_of(st, a);
+            for (int si = 0; ok; si++) {
+                Strip g;
+                if (!strip_at(a, si, g)) break;
                 const int x0 = g.x0;
                 // valid pixel range of a row segment: 8-channel sources start at x0-1, 2-channel ones at x0-2 (16-byte alignment)
                 const int lo8 = max(0, x0 - 1), hi8 = min(W, x0 + CW + 1);
@@ -298,8 +319,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
         if (p < PS) {
             int gj = 0;
 #pragma unroll 1
-            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-                const Strip g = strip_of(st, a);
+            for (int si = 0; ok; si++) {
+                Strip g;
+                if (!strip_at(a, si, g)) break;
                 const int gx = g.x0 - 1 + p;
                 const bool colok = (p < CW + 2) && gx >= 0 && gx < W;
 #pragma unroll 1
@@ -372,8 +394,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
             const uint32_t kIdesc48 = kIdescBase | (6u << 17);
             int gj = 0, go = 0;
 #pragma unroll 1
-            for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-                const Strip gs = strip_of(st, a);
+            for (int si = 0; ok; si++) {
+                Strip gs;
+                if (!strip_at(a, si, gs)) break;
                 const int R = gs.R;
 #pragma unroll 1
                 for (int j = 0; j < gs.NP; j++, gj++) {
@@ -433,8 +456,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv3x3_tcr_kernel(Args a) {
         float lmax = 0.f;
         int gj = 0, go = 0;
 #pragma unroll 1
-        for (int st = blockIdx.x; st < a.total_strips && ok; st += gridDim.x) {
-            const Strip gs = strip_of(st, a);
+        for (int si = 0; ok; si++) {
+            Strip gs;
+            if (!strip_at(a, si, gs)) break;
             // M = 64: quadrant q holds pixels 16 q .. 16 q + 15 in its first 16 lanes, the other lanes are idle
             const int gx = m64 ? (lane < 16 ? gs.x0 + quad * 16 + lane : W) : gs.x0 + quad * 32 + lane;
             const int y0 = gs.y0;

@@ -626,6 +626,35 @@ static int tcr_rows_per_strip(const hn_ctx* c, int H, int nsx, int B) {
 }
 #endif
 
+#ifdef HN_HAVE_TC
+// strips of the per-conv row-streaming kernel: uniform rounds (tcr_rows_per_strip) or, where the model predicts 3 %, balanced chunks
+// over the rows of all batch * nsx column strips (common.cuh: balanced_strip).  Returns the grid.
+static int tcr_plan_strips(const hn_ctx* c, tcr::Args& t, int B) {
+    t.nsx = (t.W + tcr::CW - 1) / tcr::CW;
+    t.rows = tcr_rows_per_strip(c, t.H, t.nsx, B);
+    t.nsy = (t.H + t.rows - 1) / t.rows;
+    t.total_strips = t.nsx * t.nsy * B;
+    const int cap = 2 * c->num_sms;       // persistent: 2 CTAs per SM
+    int tgrid = t.total_strips < cap ? t.total_strips : cap;
+    t.pdl_trig = pdl_early(c, t.total_strips, 2);
+    t.bal = 0;
+    if (c->dconv_balance >= 2) {
+        const long long rounds = (t.total_strips + tgrid - 1) / tgrid;
+        // (32-row strips at 64+ rows per SM pair a long and a short strip list per SM: what counts there is the work per SM)
+        const bool per_sm = (long long)B * t.H * t.nsx / c->num_sms >= 64;
+        const long long uniform_sm = per_sm ? ((long long)t.total_strips + c->num_sms - 1) / c->num_sms * (t.rows + 6) : 2 * rounds * (t.rows + 6);
+        const long long vt = (long long)B * t.nsx * (t.H + tcr::BAL_PAD);
+        const long long balanced = (vt + cap - 1) / cap + tcr::BAL_PAD + 2;
+        if (vt / cap >= 12 && 2 * balanced * 100 <= uniform_sm * 97) {
+            t.bal = B * t.nsx;
+            tgrid = cap;
+            t.pdl_trig = c->pdl_mode == 1 || c->pdl_mode == 2;
+        }
+    }
+    return tgrid;
+}
+#endif
+
 template <int SRC, int COUT, bool PRELU, int EPI>
 static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
     const size_t smem = conv3_smem_bytes(SRC, COUT);
@@ -652,12 +681,7 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
             t.amax_in0 = a.amax_in0; t.amax_in1 = a.amax_in1; t.amax_out = a.amax_out;
             t.error_flag = c->err_flag; t.sigma_max = 0.f; t.w_inv_scale = a.tc_inv;
             t.H = a.H; t.W = a.W;
-            t.nsx = (a.W + tcr::CW - 1) / tcr::CW;
-            t.rows = tcr_rows_per_strip(c, a.H, t.nsx, B);
-            t.nsy = (a.H + t.rows - 1) / t.rows;
-            t.total_strips = t.nsx * t.nsy * B;
-            const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;
-            t.pdl_trig = pdl_early(c, t.total_strips, 2);
+            const int tgrid = tcr_plan_strips(c, t, B);
             HN_LAUNCH_PDL(c->pdl, (tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI_STORE2>), dim3(tgrid), dim3(tcr::THREADS), tcr::smem_bytes(SRC), st, t);
             c->launches++;
             return HN_OK;
@@ -678,12 +702,7 @@ static int launch_conv3(hn_ctx* c, const Conv3Args& a, int B, cudaStream_t st) {
             t.amax_in0 = a.amax_in0; t.amax_in1 = a.amax_in1; t.amax_out = a.amax_out;
             t.error_flag = c->err_flag; t.sigma_max = c->pml > 0 ? (float)c->sigma_max : 0.f; t.w_inv_scale = a.tc_inv;
             t.H = a.H; t.W = a.W;
-            t.nsx = (a.W + tcr::CW - 1) / tcr::CW;
-            t.rows = tcr_rows_per_strip(c, a.H, t.nsx, B);
-            t.nsy = (a.H + t.rows - 1) / t.rows;
-            t.total_strips = t.nsx * t.nsy * B;
-            const int tgrid = t.total_strips < 2 * c->num_sms ? t.total_strips : 2 * c->num_sms;   // persistent: 2 CTAs per SM
-            t.pdl_trig = pdl_early(c, t.total_strips, 2);
+            const int tgrid = tcr_plan_strips(c, t, B);
             HN_LAUNCH_PDL(c->pdl, (tcr::conv3x3_tcr_kernel<SRC, PRELU, EPI>), dim3(tgrid), dim3(tcr::THREADS), tcr::smem_bytes(SRC), st, t);
             c->launches++;
             return HN_OK;
