@@ -16,8 +16,9 @@ solver without the built library or without a Blackwell GPU raises.
 from .checkpoint import HParams, load_checkpoint
 from .solver import HybridNet, IterativeSolver
 from .source import SourceModule
+from .training import Experience, ReplayBuffer
 from ._lib import HelmnetLib, LibraryMissingError, lib_path
 
 __all__ = ["IterativeSolver", "HybridNet", "SourceModule", "HParams", "load_checkpoint", "HelmnetLib",
-           "LibraryMissingError", "lib_path"]
+           "LibraryMissingError", "lib_path", "Experience", "ReplayBuffer"]
 __version__ = "0.1.0"

@@ -604,6 +604,33 @@ def test_two_sgd_steps_with_per_sample_sources(f_weights):
     assert e_loss < 1e-4 and worst < 3e-4
 
 
+def test_fit_loop_on_the_gpu():
+    """helmnet_b200/training.py on cuda:0: fill the device-resident replay buffer, two epochs of training_step + backward + clip +
+    Adam (the reference's training loop without Lightning, hybridnet.py:192-218, 250-284, 385-505); the buffer's slots advance or
+    restart, the weights move, everything stays finite.  (training_step itself is pinned on the reference's own training_step in
+    tests/test_training_driver.py.)"""
+    import random
+    import numpy as np
+    from helmnet_b200 import IterativeSolver, training as T
+    from helmnet_b200.synthetic import synthetic_sos
+    s = IterativeSolver.load_from_checkpoint(CKPT, strict=False, test_data_path=None)
+    s.to("cuda:0")
+    s.hparams.source_location = [20, 24]
+    s.set_domain_size(48, source_location=[20, 24])
+    s.hparams.batch_size, s.hparams.buffer_size, s.hparams.unrolling_steps, s.hparams.learning_rate = 4, 8, 3, 1e-5
+    np.random.seed(2); random.seed(2); torch.manual_seed(2)
+    sos = synthetic_sos(8, 48, seed=4)
+    buf = T.ReplayBuffer(8)
+    w0 = s.f.weight_blob().clone()
+    hist = T.fit(s, sos, epochs=3, buffer=buf)
+    s.sync_check()
+    assert len(hist) == 3 and all(np.isfinite(h) for h in hist)
+    assert buf._store["wavefield"].is_cuda and torch.isfinite(buf._store["wavefield"]).all()
+    assert any(it not in (0, 10, 20, 30, 40, 50, 60, 70) for it in buf.iterations) or sorted(buf.iterations) != [10 * i for i in range(8)]
+    assert float((s.f.weight_blob() - w0).abs().max()) > 0
+    record("fit_loop", losses=[float(h) for h in hist])
+
+
 def test_training_step_time_at_the_reference_configuration(cuda_trainable):
     """The reference's training configuration (checkpoint hparams: 96 x 96, batch 32, unrolling_steps 10): forward + backward of
     one training_step through this build, beside the same graph in eager PyTorch (cuDNN + cuFFT, TF32 off) on the same GPU."""
