@@ -617,7 +617,8 @@ def test_fit_loop_on_the_gpu():
     s.to("cuda:0")
     s.hparams.source_location = [20, 24]
     s.set_domain_size(48, source_location=[20, 24])
-    s.hparams.batch_size, s.hparams.buffer_size, s.hparams.unrolling_steps, s.hparams.learning_rate = 4, 8, 3, 1e-5
+    s.hparams.batch_size, s.hparams.buffer_size, s.hparams.unrolling_steps = 4, 8, 3
+    s.hparams.learning_rate, s.hparams.minimum_learning_rate = 1e-5, 1e-6
     np.random.seed(2); random.seed(2); torch.manual_seed(2)
     sos = synthetic_sos(8, 48, seed=4)
     buf = T.ReplayBuffer(8)
