@@ -62,11 +62,17 @@ struct Args {
     int rows_o;                 // output rows per strip: small batches take short strips so that every SM gets one
     int nsx, nsy, total_strips;
     int bal;                    // != 0 (nsx == 1 only): balanced strips over the output rows of `bal` images (common.cuh: balanced_strip)
+    // Narrow images side by side (output width <= 62, nsx == 1): `pack` images share ONE M = 128 MMA.  Image k of a group owns the
+    // operand entries [k S, k S + S) of each parity plane, S = W/2 + 2: two zero entries (pixels -4 .. -1), then its W/2 data entries;
+    // the two zero entries its right-hand taps need are the next image's left-hand ones.  GEMM row m = k S + ox, every tap stays a
+    // pure start-address shift.  The strip walk then runs over groups of images ("image" b of strip_of / balanced_strip = group b).
+    int pack, pack_s, batch;
 };
 
 struct Strip {
     int ox0, oy0, Ro, NP;
-    size_t img_in, img_out;
+    int nimg;                   // images of this strip's group (1 without packing)
+    size_t img_in, img_out;     // first pixel of the (first) image
 };
 __device__ __forceinline__ Strip strip_of(int st, const Args& a) {
     Strip g;
@@ -76,8 +82,10 @@ __device__ __forceinline__ Strip strip_of(int st, const Args& a) {
     g.oy0 = sy * a.rows_o;
     g.Ro = min(a.rows_o, (a.H >> 1) - g.oy0);
     g.NP = g.Ro + 3;            // input row pairs: rows k = 0 .. 2 Ro + 5, image row 2 oy0 - 3 + k
-    g.img_in = (size_t)b * a.H * a.W;
-    g.img_out = (size_t)b * (a.H >> 1) * (a.W >> 1);
+    const int img0 = a.pack > 0 ? b * a.pack : b;
+    g.nimg = a.pack > 0 ? min(a.pack, a.batch - img0) : 1;
+    g.img_in = (size_t)img0 * a.H * a.W;
+    g.img_out = (size_t)img0 * (a.H >> 1) * (a.W >> 1);
     return g;
 }
 constexpr int BAL_PAD = 6;     // a strip start costs ~5 row steps (3 extra input row pairs + fill)
@@ -95,15 +103,17 @@ __device__ __forceinline__ bool strip_at(const Args& a, int i, Strip& g) {
     g.oy0 = oy0;
     g.Ro = Ro;
     g.NP = Ro + 3;
-    g.img_in = (size_t)b * a.H * a.W;
-    g.img_out = (size_t)b * (a.H >> 1) * (a.W >> 1);
+    const int img0 = a.pack > 0 ? b * a.pack : b;
+    g.nimg = a.pack > 0 ? min(a.pack, a.batch - img0) : 1;
+    g.img_in = (size_t)img0 * a.H * a.W;
+    g.img_out = (size_t)img0 * (a.H >> 1) * (a.W >> 1);
     return true;
 }
 
 __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
     // M = 64 when the output is no wider than 64 pixels (half the A-operand fetch; accumulator row i then sits in lane
     // 32 (i / 16) + i % 16, see conv_tcr.cuh)
-    const bool m64 = (a.W >> 1) <= 64;
+    const bool m64 = (a.W >> 1) <= 64 && a.pack == 0;
     const uint32_t kIdescBase = (1u << 4) | ((m64 ? (64u >> 4) : (128u >> 4)) << 24);
     extern __shared__ __align__(128) uint8_t smem_tcd[];
     uint8_t* stage = smem_tcd;                                          // [NSP][2] fp32 rows
@@ -120,7 +130,7 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = a.H, W = a.W, Wo = W >> 1;
     // staging ring geometry: rows of up to 132 staged pixels fit half a slot
-    const bool narrow = W <= 128;
+    const bool narrow = W <= 128 && a.pack == 0;      // (packed groups fill a whole staging row)
     const int nsp_sh = narrow ? 2 : 1, nsp_mask = (1 << nsp_sh) - 1;       // ring depth 4 or 2 (row pairs)
     const uint32_t row_st = narrow ? ROW_ST_BYTES / 2 : ROW_ST_BYTES;
 
@@ -184,6 +194,7 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
                 const int xb = 2 * g.ox0 - 4;                               // first staged pixel (even)
                 const int lo = max(0, xb), hi = min(W, xb + 2 * PS - 8);    // 264 pixels cover every tap of 128 outputs
                 const uint32_t rb = (uint32_t)(hi - lo) * 32u;
+                const size_t img_px = (size_t)H * W;
 #pragma unroll 1
                 for (int j = 0; j < g.NP; j++, gj++) {
                     const int sidx = gj & nsp_mask;
@@ -194,12 +205,15 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
                         mbar_arrive(stage_full + sidx);
                         continue;
                     }
-                    mbar_arrive_expect_tx(stage_full + sidx, ((uint32_t)v0 + (uint32_t)v1) * rb);
+                    mbar_arrive_expect_tx(stage_full + sidx, ((uint32_t)v0 + (uint32_t)v1) * rb * (uint32_t)g.nimg);
 #pragma unroll
                     for (int t = 0; t < 2; t++) {
                         if (!(t == 0 ? v0 : v1)) continue;
                         uint8_t* dst = stage + (size_t)(sidx * 2 + t) * row_st;
-                        tma_load_1d(dst + (lo - xb) * 32, a.in + (g.img_in + (size_t)(gy0 + t) * W + lo) * 8, rb, stage_full + sidx);
+                        // (packed: image k's pixel 0 sits at entry k S + 2 of the parity planes = byte (k S + 2) * 64 of the staged row)
+                        for (int k = 0; k < g.nimg; k++)
+                            tma_load_1d(dst + (size_t)k * a.pack_s * 64 + (lo - xb) * 32, a.in + (g.img_in + k * img_px + (size_t)(gy0 + t) * W + lo) * 8, rb,
+                                        stage_full + sidx);
                     }
                 }
             }
@@ -218,8 +232,10 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
                 Strip g;
                 if (!strip_at(a, si, g)) break;
                 const int xb = 2 * g.ox0 - 4;
-                const int gxe = xb + 2 * p, gxo = gxe + 1;
-                const bool oke = (p < PS - 4) && gxe >= 0 && gxe < W, oko = (p < PS - 4) && gxo >= 0 && gxo < W;
+                const int kimg = a.pack > 0 ? p / a.pack_s : 0;                 // packed: entry p belongs to image kimg of the group
+                const int gxe = xb + 2 * (p - kimg * a.pack_s), gxo = gxe + 1;
+                const bool mine = (p < PS - 4) && kimg < g.nimg;
+                const bool oke = mine && gxe >= 0 && gxe < W, oko = mine && gxo >= 0 && gxo < W;
 #pragma unroll 1
                 for (int j = 0; j < g.NP; j++, gj++) {
                     const int sidx = gj & nsp_mask, s = gj % SRP;
@@ -320,7 +336,13 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
         for (int si = 0; ok; si++) {
             Strip gs;
             if (!strip_at(a, si, gs)) break;
-            const int ox = m64 ? (lane < 16 ? gs.ox0 + quad * 16 + lane : Wo) : gs.ox0 + quad * 32 + lane;
+            int ox = m64 ? (lane < 16 ? gs.ox0 + quad * 16 + lane : Wo) : gs.ox0 + quad * 32 + lane;
+            size_t img_out = gs.img_out;
+            if (a.pack > 0) {            // GEMM row m = k S + ox of image k of the group
+                const int m = quad * 32 + lane, k = m / a.pack_s;
+                ox = k < gs.nimg ? m - k * a.pack_s : Wo;
+                img_out += (size_t)k * (H >> 1) * Wo;
+            }
 #pragma unroll 1
             for (int oyl = 0; oyl < gs.Ro; oyl++) {
                 const int gjd = gj + oyl + 3;                  // input pair that completes output row oyl
@@ -348,7 +370,7 @@ __global__ void __launch_bounds__(THREADS, 2) down_tcr_kernel(Args a) {
                         o[c] = fmaf(fmaf(__uint_as_float(v[8 + c]), 1.f / 2048.f, __uint_as_float(v[c])), out_scale, a.bias[c]);
                         lmax = fmaxf(lmax, fabsf(o[c]));
                     }
-                    float4* dst = reinterpret_cast<float4*>(a.out + (gs.img_out + (size_t)(gs.oy0 + oyl) * Wo + ox) * 8);
+                    float4* dst = reinterpret_cast<float4*>(a.out + (img_out + (size_t)(gs.oy0 + oyl) * Wo + ox) * 8);
                     st_nhwc8(reinterpret_cast<float*>(dst), o);
                 }
             }

@@ -58,11 +58,15 @@ struct Args {
     int nsx, nsy, total_strips;
     int rows_i;                 // input rows per strip (even)
     int bal;                    // != 0 (nsx == 1 only): balanced strips over the input rows of `bal` images (common.cuh: balanced_strip)
+    // Narrow images side by side (input width <= 62, nsx == 1): `pack` images share ONE M = 128 MMA (see conv_tcr_down.cuh).  Image k
+    // of a group owns the operand entries [k S, k S + S), S = Wi + 2: two zero cells, then its Wi cells; GEMM row m = k S + cell.
+    int pack, pack_s, batch;
 };
 
 struct Strip {
     int x0, iy0, Ri, NP;
-    size_t img_in, img_out;
+    int nimg;                   // images of this strip's group (1 without packing)
+    size_t img_in, img_out;     // first pixel of the (first) image
 };
 __device__ __forceinline__ Strip strip_of(int st, const Args& a) {
     Strip g;
@@ -72,7 +76,9 @@ __device__ __forceinline__ Strip strip_of(int st, const Args& a) {
     g.iy0 = sy * a.rows_i;
     g.Ri = min(a.rows_i, a.Hi - g.iy0);   // even
     g.NP = (g.Ri + 4) / 2;                // input rows k = 0 .. Ri + 3, image row iy0 - 2 + k
-    g.img_in = (size_t)b * a.Hi * a.Wi;
+    const int img0 = a.pack > 0 ? b * a.pack : b;
+    g.nimg = a.pack > 0 ? min(a.pack, a.batch - img0) : 1;
+    g.img_in = (size_t)img0 * a.Hi * a.Wi;
     g.img_out = g.img_in * 4;
     return g;
 }
@@ -91,14 +97,16 @@ __device__ __forceinline__ bool strip_at(const Args& a, int i, Strip& g) {
     g.iy0 = iy0;
     g.Ri = Ri;
     g.NP = (Ri + 4) / 2;
-    g.img_in = (size_t)b * a.Hi * a.Wi;
+    const int img0 = a.pack > 0 ? b * a.pack : b;
+    g.nimg = a.pack > 0 ? min(a.pack, a.batch - img0) : 1;
+    g.img_in = (size_t)img0 * a.Hi * a.Wi;
     g.img_out = g.img_in * 4;
     return true;
 }
 
 __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
     // M = 64 when the input is no wider than 64 cells (accumulator row i then sits in lane 32 (i / 16) + i % 16, see conv_tcr.cuh)
-    const bool m64 = a.Wi <= 64;
+    const bool m64 = a.Wi <= 64 && a.pack == 0;
     const uint32_t kIdescBase = (1u << 4) | ((m64 ? (64u >> 4) : (128u >> 4)) << 24);
     extern __shared__ __align__(128) uint8_t smem_tcu[];
     uint8_t* stage = smem_tcu;
@@ -184,12 +192,15 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
                         mbar_arrive(stage_full + sidx);
                         continue;
                     }
-                    mbar_arrive_expect_tx(stage_full + sidx, ((uint32_t)v0 + (uint32_t)v1) * rb);
+                    mbar_arrive_expect_tx(stage_full + sidx, ((uint32_t)v0 + (uint32_t)v1) * rb * (uint32_t)g.nimg);
 #pragma unroll
                     for (int t = 0; t < 2; t++) {
                         if (!(t == 0 ? v0 : v1)) continue;
                         uint8_t* dst = stage + (size_t)(sidx * 2 + t) * ROW_ST_BYTES;
-                        tma_load_1d(dst + (lo - (g.x0 - 2)) * 32, a.in + (g.img_in + (size_t)(gy0 + t) * Wi + lo) * 8, rb, stage_full + sidx);
+                        // (packed: image k's cell 0 sits at entry k S + 2 of the staged row)
+                        for (int k = 0; k < g.nimg; k++)
+                            tma_load_1d(dst + (size_t)k * a.pack_s * 32 + (lo - (g.x0 - 2)) * 32,
+                                        a.in + (g.img_in + (size_t)k * Hi * Wi + (size_t)(gy0 + t) * Wi + lo) * 8, rb, stage_full + sidx);
                     }
                 }
             }
@@ -205,8 +216,9 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
             for (int si = 0; ok; si++) {
                 Strip g;
                 if (!strip_at(a, si, g)) break;
-                const int gx = g.x0 - 2 + p;
-                const bool colok = (p < CW + 4) && gx >= 0 && gx < Wi;
+                const int kimg = a.pack > 0 ? p / a.pack_s : 0;                 // packed: entry p belongs to image kimg of the group
+                const int gx = g.x0 - 2 + (p - kimg * a.pack_s);
+                const bool colok = (p < CW + 4) && kimg < g.nimg && gx >= 0 && gx < Wi;
 #pragma unroll 1
                 for (int j = 0; j < g.NP; j++, gj++) {
                     const int sidx = gj % NSP, s = gj % SRP;
@@ -294,7 +306,13 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
         for (int si = 0; ok; si++) {
             Strip gs;
             if (!strip_at(a, si, gs)) break;
-            const int cell = m64 ? (lane < 16 ? gs.x0 + quad * 16 + lane : Wi) : gs.x0 + quad * 32 + lane;
+            int cell = m64 ? (lane < 16 ? gs.x0 + quad * 16 + lane : Wi) : gs.x0 + quad * 32 + lane;
+            size_t img_out = gs.img_out;
+            if (a.pack > 0) {            // GEMM row m = k S + cell of image k of the group
+                const int m = quad * 32 + lane, k = m / a.pack_s;
+                cell = k < gs.nimg ? m - k * a.pack_s : Wi;
+                img_out += (size_t)k * 4 * Hi * Wi;
+            }
             const int Ro = 2 * gs.Ri;
 #pragma unroll 1
             for (int es = 0; es < Ro / 4; es++) {
@@ -328,7 +346,7 @@ __global__ void __launch_bounds__(THREADS, 1) up_tcr_kernel(Args a) {
                     if (cell < Wi) {
 #pragma unroll
                         for (int t = 0; t < 2; t++) {
-                            float4* dst = reinterpret_cast<float4*>(a.out + (gs.img_out + (size_t)(2 * gs.iy0 + oyl + t) * Wo + 2 * cell) * 8);
+                            float4* dst = reinterpret_cast<float4*>(a.out + (img_out + (size_t)(2 * gs.iy0 + oyl + t) * Wo + 2 * cell) * 8);
 #pragma unroll
                             for (int px = 0; px < 2; px++) {
                                 float o[8];

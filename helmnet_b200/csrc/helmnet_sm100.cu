@@ -148,6 +148,8 @@ struct hn_ctx {
     bool tcf_any_width = true; // fused DoubleConv kernels for every even width up to 256 (not only 32 / 64 / 128 / 256)
     int tcf_min_width = 6;     // (6: the bottom DoubleConv of the 96^2 training-domain size)
     int dconv_min_rows = 4;    // shortest strip of the fused DoubleConv kernels (small batches: more, shorter strips fill more SMs)
+    int pack_penalty = 12;     // per cent a pipeline step of those kernels gets slower per additional packed image (pick_pack)
+    bool pack_narrow = true;   // down- / up-sampling of levels at most 62 pixels wide: several images per M = 128 MMA (HELMNET_PACK_NARROW=0: off)
     int dconv_balance = 2;     // balanced strips where the model predicts a gain (HELMNET_DCONV_BALANCE: 0 off, 1 the fused DoubleConv
                                // kernels only, 2 also the down- / up-sampling kernels)
     bool fuse_bottom = true;   // decode[4] (the 8 -> 8 -> 8 DoubleConv at the bottom of the UNet) through the fused DoubleConv kernel
@@ -783,6 +785,29 @@ static int set_smem_attrs(hn_ctx* c) {
 }
 #endif
 
+#ifdef HN_HAVE_TC
+// Images per M = 128 MMA of a narrow down- / up-sampling level (conv_tcr_down.cuh: Args::pack), 0 = one image per MMA as before.
+// These launches are bound by the latency of a pipeline step, not by its work: packing g images cuts the steps per CTA only while
+// there are more rows than CTA slots, and every packed image makes a step a little heavier (2 more TMA loads, M = 128 instead of
+// 64).  Model: (rows per CTA slot + pad) x (1 + penalty (g - 1)) with whole even strips of at least two rows; measured on B200
+// (profiles/r2_ab_runs.txt): full packing gains 4-5 % per iteration at 256^2 x 256 and loses 7 % at 64^2 x 32, where a level has
+// fewer rows than slots to begin with.
+static int pick_pack(const hn_ctx* c, int B, int width, int rows, int cap, int pad) {
+    if (!c->pack_narrow || width > 62 || B < 2) return 0;
+    const int s_ = width + 2, gmax = (128 - width) / s_ + 1;
+    int best = 1;
+    long long best_cost = -1;
+    for (int g = 1; g <= gmax && g <= B; g++) {
+        const long long groups = (B + g - 1) / g;
+        long long R = (groups * rows + cap - 1) / cap;
+        R = R < 2 ? 2 : ((R + 1) & ~1ll);
+        const long long cost = (R + pad) * (100 + (long long)c->pack_penalty * (g - 1));
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = g; }
+    }
+    return best > 1 ? best : 0;
+}
+#endif
+
 static int launch_down(hn_ctx* c, int d, int B, cudaStream_t st) {
     const Weights& W = c->W;
     const int r = c->r[d];
@@ -813,6 +838,10 @@ static int launch_down(hn_ctx* c, int d, int B, cudaStream_t st) {
         t.H = r;
         t.W = r;
         t.nsx = (r / 2 + tcr::CW - 1) / tcr::CW;
+        // narrow levels: several images side by side in one M = 128 MMA (conv_tcr_down.cuh: Args::pack); the strip walk below then
+        // runs over groups of images
+        t.pack = pick_pack(c, B, r / 2, r / 2, 2 * c->num_sms, 5); t.pack_s = r / 2 + 2; t.batch = B;
+        if (t.pack > 0) B = (B + t.pack - 1) / t.pack;
         {
             // output rows per strip: whole rounds of equal strips over two CTAs per SM; a strip of R output rows streams
             // R + 3 input row pairs (+ ~2 steps of pipeline fill).  Small batches get short strips (one per CTA slot) instead
@@ -891,6 +920,9 @@ static int launch_up(hn_ctx* c, int d, int B, cudaStream_t st) {
         t.Hi = r / 2;
         t.Wi = r / 2;
         t.nsx = (r / 2 + tcr::CW - 1) / tcr::CW;
+        // narrow levels: several images side by side in one M = 128 MMA (conv_tcr_up.cuh: Args::pack)
+        t.pack = pick_pack(c, B, r / 2, r / 2, c->num_sms, 6); t.pack_s = r / 2 + 2; t.batch = B;
+        if (t.pack > 0) B = (B + t.pack - 1) / t.pack;
         {
             // input rows per strip: whole rounds of equal strips over one CTA per SM; a strip of R rows streams R + 4 rows
             // (+ ~2 row steps of pipeline fill)
@@ -1325,6 +1357,8 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     if (const char* pv = getenv("HELMNET_FUSE_BOTTOM")) c->fuse_bottom = atoi(pv) != 0;
     if (const char* pv = getenv("HELMNET_SIDE_STATE")) c->side_cfg = atoi(pv);
     if (const char* pv = getenv("HELMNET_DCONV_BALANCE")) c->dconv_balance = atoi(pv);
+    if (const char* pv = getenv("HELMNET_PACK_NARROW")) c->pack_narrow = atoi(pv) != 0;
+    if (const char* pv = getenv("HELMNET_PACK_PENALTY")) c->pack_penalty = atoi(pv);
 #ifndef HN_EMU
     if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail(HN_ERR_CUDA, "cudaStreamCreate failed"));
     for (int d = 0; d < kDepth; d++)
