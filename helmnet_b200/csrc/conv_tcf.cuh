@@ -118,6 +118,12 @@ struct Args {
     int spi;                    // strips per image
     int total_strips;
     int bal;                    // != 0: balanced strips (strip_of): the batch size; the grid then is one chunk of rows per CTA
+    // Narrow images side by side (the 128-pixel variant, images at most 62 pixels wide; not for SRC_INC / EPI_OUTC): `pack` images of a
+    // group share the GEMM rows of one M = 128 MMA.  Image k owns the columns [k S, k S + W) of the kernel's row, S = W + 2 (even, so
+    // that every staged segment stays 16-byte aligned); the columns between two images are never written by the converters /
+    // epilogue 1, so they keep their zeros and are the x zero padding of both neighbours.  The strip walk runs over groups
+    // ("image" b of strip_of = group b).
+    int pack, pack_s, batch;
 };
 
 // Strip i of this CTA (image b, first output row y0, R rows); false when it has none.
@@ -127,6 +133,20 @@ struct Args {
 //             line: every CTA gets the same rows + BAL_PAD * strips, whatever the ratio of images to SMs (one image boundary inside a
 //             chunk costs that CTA BAL_PAD rows of work less).  All boundaries are even.
 constexpr int BAL_PAD = 8;
+// column x of the kernel's row -> (image k of the group, column xl of that image); false for the columns between / beyond the images
+__device__ __forceinline__ bool packed_column(const Args& a, int x, int nimg, int& k, int& xl) {
+    if (a.pack == 0) {
+        k = 0;
+        xl = x;
+        return x < a.W;
+    }
+    k = x / a.pack_s;
+    xl = x - k * a.pack_s;
+    return k < nimg && xl < a.W;
+}
+__device__ __forceinline__ int group_images(const Args& a, int b) { return a.pack == 0 ? 1 : min(a.pack, a.batch - b * a.pack); }
+__device__ __forceinline__ size_t group_first_pixel(const Args& a, int b) { return (size_t)(a.pack == 0 ? b : b * a.pack) * a.H * a.W; }
+
 __device__ __forceinline__ bool strip_of(const Args& a, int i, int& b, int& y0, int& R) {
     if (a.bal == 0) {
         const int st = (int)blockIdx.x + i * (int)gridDim.x;
@@ -371,8 +391,10 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
 #pragma unroll 1
             for (int si = 0, b, y0, R; ok && strip_of(a, si, b, y0, R); si++) {
                 const int NP1 = (R + 4) / 2;
-                const size_t img = (size_t)b * H * Wa;
-                const uint32_t row_tx = (uint32_t)Wa * (uint32_t)(SROW / W);   // bytes one image row brings in
+                const size_t img = group_first_pixel(a, b);
+                const int nimg = group_images(a, b);
+                const size_t img_px = (size_t)H * Wa;
+                const uint32_t row_tx = (uint32_t)Wa * (uint32_t)(SROW / W) * (uint32_t)nimg;   // bytes one row of the group brings in
 #pragma unroll 1
                 for (int j = 0; j < NP1; j++, gj++) {
                     const int sidx = gj % NSP;
@@ -387,19 +409,23 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
 #pragma unroll
                     for (int t = 0; t < 2; t++) {
                         if (!(t == 0 ? v0 : v1)) continue;
-                        uint8_t* dst = stage + (size_t)(sidx * 2 + t) * SROW;
-                        const size_t rowpix = img + (size_t)(gy0 + t) * Wa;
-                        if constexpr (SRC == SRC_INC) {
-                            tma_load_1d(dst, a.inA + rowpix * 2, Wa * 8, stage_full + sidx);
-                            tma_load_1d(dst + W * 8, a.inB + rowpix * 2, Wa * 8, stage_full + sidx);
-                        } else if constexpr (SRC == SRC_A8) {
-                            tma_load_1d(dst, a.inA + rowpix * 8, Wa * 32, stage_full + sidx);
-                        } else if constexpr (SRC == SRC_A8_B8) {
-                            tma_load_1d(dst, a.inA + rowpix * 8, Wa * 32, stage_full + sidx);
-                            tma_load_1d(dst + W * 32, a.inB + rowpix * 8, Wa * 32, stage_full + sidx);
-                        } else {
-                            tma_load_1d(dst, a.inA + rowpix * 8, Wa * 32, stage_full + sidx);
-                            tma_load_1d(dst + W * 32, a.inB + rowpix * 2, Wa * 8, stage_full + sidx);
+                        uint8_t* dst0 = stage + (size_t)(sidx * 2 + t) * SROW;
+                        for (int k = 0; k < nimg; k++) {      // (packed: image k of the group lands at column k S of the staged row)
+                            const size_t rowpix = img + k * img_px + (size_t)(gy0 + t) * Wa;
+                            const int xk = k * a.pack_s;
+                            uint8_t* dst = dst0;
+                            if constexpr (SRC == SRC_INC) {
+                                tma_load_1d(dst, a.inA + rowpix * 2, Wa * 8, stage_full + sidx);
+                                tma_load_1d(dst + W * 8, a.inB + rowpix * 2, Wa * 8, stage_full + sidx);
+                            } else if constexpr (SRC == SRC_A8) {
+                                tma_load_1d(dst + xk * 32, a.inA + rowpix * 8, Wa * 32, stage_full + sidx);
+                            } else if constexpr (SRC == SRC_A8_B8) {
+                                tma_load_1d(dst + xk * 32, a.inA + rowpix * 8, Wa * 32, stage_full + sidx);
+                                tma_load_1d(dst + W * 32 + xk * 32, a.inB + rowpix * 8, Wa * 32, stage_full + sidx);
+                            } else {
+                                tma_load_1d(dst + xk * 32, a.inA + rowpix * 8, Wa * 32, stage_full + sidx);
+                                tma_load_1d(dst + W * 32 + xk * 8, a.inB + rowpix * 2, Wa * 8, stage_full + sidx);
+                            }
                         }
                     }
                 }
@@ -409,13 +435,17 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
     } else if (warp < CONV_WARPS) {
         // =============================== converters: thread <-> image column x = tid ================================
         const int x = tid;
-        const bool live = x < Wa;     // columns beyond the image keep zero operands
+        bool live = x < Wa;           // columns beyond the image (packed: between / beyond the images of the group) keep zero operands
         const float sig_x = (SRC == SRC_INC && live) ? __ldg(a.sigma + x) : 0.f;
         const int sw16 = ((x >> 2) & 1) * 16;
         int gj = 0;
 #pragma unroll 1
         for (int si = 0, b, y0, R; ok && strip_of(a, si, b, y0, R); si++) {
             const int NP1 = (R + 4) / 2;
+            if (a.pack > 0) {
+                int kk, xl;
+                live = packed_column(a, x, group_images(a, b), kk, xl);
+            }
 #pragma unroll 1
             for (int j = 0; j < NP1; j++, gj++) {
                 const int sidx = gj % NSP, s = gj % SRP1;
@@ -550,12 +580,16 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
         // =============================== epilogue 1: accumulators -> PReLU -> operand ring A2 ========================
         const int half = (warp - EPI1_WARP0) >> 2, quad = warp & 3;
         const int x = NH <= 0 ? quad * 16 + (lane & 15) : half * 128 + quad * 32 + lane;
-        const bool act = (NH > 0 || (lane < 16 && quad * 16 < W)) && x < Wa;   // M = 64: 16 accumulator rows per TMEM lane quadrant
+        bool act = (NH > 0 || (lane < 16 && quad * 16 < W)) && x < Wa;   // M = 64: 16 accumulator rows per TMEM lane quadrant
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + ACC1 + (uint32_t)(half * TR * NC);
         int gj = 0, gmp = 0;
 #pragma unroll 1
         for (int si = 0, b, y0, R; ok && strip_of(a, si, b, y0, R); si++) {
             const int NP1 = (R + 4) / 2, NM = (R + 2) / 2;
+            if (a.pack > 0) {
+                int kk, xl;
+                act = packed_column(a, x, group_images(a, b), kk, xl);
+            }
 #pragma unroll 1
             for (int p = 0; p < NM; p++) {
                 const int gjd = gj + p + 1;                 // input pair that completes mid rows 2p, 2p+1
@@ -601,14 +635,21 @@ __global__ void __launch_bounds__(threads(NH), NH == 2 ? 1 : 2) dconv_tcf_kernel
         // =============================== epilogue 2: accumulators -> bias / outc / update -> HBM =====================
         const int half = (warp - EPI2_WARP0) >> 2, quad = warp & 3;
         const int x = NH <= 0 ? quad * 16 + (lane & 15) : half * 128 + quad * 32 + lane;
-        const bool act = (NH > 0 || (lane < 16 && quad * 16 < W)) && x < Wa;
+        bool act = (NH > 0 || (lane < 16 && quad * 16 < W)) && x < Wa;
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + ACC2 + (uint32_t)(half * TR * NC);
         float lmax = 0.f;
         int gmp = 0, gop = 0;
+        const int xcol = x;             // column of the kernel's row; `x` becomes the column inside this thread's image when packed
 #pragma unroll 1
         for (int si = 0, b, y0, R; ok && strip_of(a, si, b, y0, R); si++) {
             const int NM = (R + 2) / 2;
-            const size_t img = (size_t)b * H * Wa;
+            size_t img = group_first_pixel(a, b);
+            int x = xcol;
+            if (a.pack > 0) {
+                int kk;
+                act = packed_column(a, xcol, group_images(a, b), kk, x);
+                img += (size_t)kk * H * Wa;
+            }
 #pragma unroll 1
             for (int q = 0; q < R / 2; q++) {
                 const int ya = 2 * q;

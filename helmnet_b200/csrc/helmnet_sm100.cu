@@ -149,7 +149,9 @@ struct hn_ctx {
     int tcf_min_width = 6;     // (6: the bottom DoubleConv of the 96^2 training-domain size)
     int dconv_min_rows = 4;    // shortest strip of the fused DoubleConv kernels (small batches: more, shorter strips fill more SMs)
     int pack_penalty = 12;     // per cent a pipeline step of those kernels gets slower per additional packed image (pick_pack)
-    bool pack_narrow = true;   // down- / up-sampling of levels at most 62 pixels wide: several images per M = 128 MMA (HELMNET_PACK_NARROW=0: off)
+    int pack_narrow = 1;       // levels at most 62 pixels wide: several images per M = 128 MMA (HELMNET_PACK_NARROW: 0 off, 1 the down- /
+                               // up-sampling kernels (default), 2 also the fused DoubleConv kernels -- measured: -0.5 .. -1.2 % per iteration
+                               // at 256^2 x 32 / x 64 / 128^2 x 64, +1 % at 256^2 x 256, so it stays opt-in)
     int dconv_balance = 2;     // balanced strips where the model predicts a gain (HELMNET_DCONV_BALANCE: 0 off, 1 the fused DoubleConv
                                // kernels only, 2 also the down- / up-sampling kernels)
     bool fuse_bottom = true;   // decode[4] (the 8 -> 8 -> 8 DoubleConv at the bottom of the UNet) through the fused DoubleConv kernel
@@ -1053,6 +1055,18 @@ static int launch_dconv(hn_ctx* c, const ConvW (&w)[2], const float* inA, const 
     t.mid_l1 = w[0].l1; t.mid_bmax = w[0].bmax;
     t.H = r;
     t.W = r;
+    // narrow levels: several images side by side in the 128-pixel variant (conv_tcf.cuh: Args::pack), picked by the step model
+    if constexpr (SRC != SRC_INC && EPI != EPI_OUTC) {
+        if (c->pack_narrow >= 2) {
+            const int g = pick_pack(c, B, r, r, 2 * c->num_sms, 7);
+            if (g > 1) {
+                t.pack = g;
+                t.pack_s = r + 2;
+                t.batch = B;
+                return launch_dconv_nh<SRC, 1, EPI>(c, t, (B + g - 1) / g, st);
+            }
+        }
+    }
     if (r > 128) return launch_dconv_nh<SRC, 2, EPI>(c, t, B, st);
     if (r > 64) return launch_dconv_nh<SRC, 1, EPI>(c, t, B, st);
     if (r > 32) return launch_dconv_nh<SRC, 0, EPI>(c, t, B, st);
@@ -1357,7 +1371,7 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     if (const char* pv = getenv("HELMNET_FUSE_BOTTOM")) c->fuse_bottom = atoi(pv) != 0;
     if (const char* pv = getenv("HELMNET_SIDE_STATE")) c->side_cfg = atoi(pv);
     if (const char* pv = getenv("HELMNET_DCONV_BALANCE")) c->dconv_balance = atoi(pv);
-    if (const char* pv = getenv("HELMNET_PACK_NARROW")) c->pack_narrow = atoi(pv) != 0;
+    if (const char* pv = getenv("HELMNET_PACK_NARROW")) c->pack_narrow = atoi(pv);
     if (const char* pv = getenv("HELMNET_PACK_PENALTY")) c->pack_penalty = atoi(pv);
 #ifndef HN_EMU
     if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail(HN_ERR_CUDA, "cudaStreamCreate failed"));

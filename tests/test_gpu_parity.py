@@ -518,6 +518,32 @@ def test_balanced_strips_are_bit_identical(_cuda_solver_base, n, b, monkeypatch)
     assert rel_l2(outs[1][1], outs[0][1]) < 1e-6
 
 
+@pytest.mark.parametrize("n,b", [(64, 40), (96, 37), (256, 9)])
+def test_packed_narrow_levels_are_bit_identical(_cuda_solver_base, n, b, monkeypatch):
+    """Several narrow images side by side in one M = 128 MMA (conv_tcr_down / conv_tcr_up: HELMNET_PACK_NARROW=1, the default; the
+    fused DoubleConv kernels as well: =2) against one image per MMA (=0): every pixel sees the same operands in the same order, the
+    columns between the images only ever hold zeros, so the wavefields must be bit-identical.  The batch sizes leave a partly
+    filled last group at every level."""
+    s = _cuda_solver_base
+    s.set_engine(2)
+    g = torch.Generator().manual_seed(n + b)
+    sos = (1.0 + torch.rand(b, 1, n, n, generator=g)).cuda()
+    outs = []
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("HELMNET_PACK_NARROW", mode)
+        s._release_ctx()
+        s.set_domain_size(n, source_location=[n // 8, n // 2])
+        out = s.forward(sos, num_iterations=3)
+        s.sync_check()
+        outs.append((out["wavefields"][0].clone(), out["residual_rmse"].clone()))
+    monkeypatch.delenv("HELMNET_PACK_NARROW", raising=False)
+    s._release_ctx()
+    assert torch.isfinite(outs[0][0]).all()
+    for wf, rm in outs[1:]:
+        assert torch.equal(wf, outs[0][0])
+        assert rel_l2(rm, outs[0][1]) < 1e-6
+
+
 def test_large_batch_strip_paths_match_small_batch(_cuda_solver_base):
     """The strip heights of the down / up / per-conv kernels and the launch options (PDL, side branch) are picked from the batch
     size: a batch of 96 takes the throughput-regime choices (32-row strips, no side branch), a batch of 3 the small-solve ones.
