@@ -29,4 +29,14 @@ for n, b, iters in ((64, 3, 3), (96, 2, 2), (256, 2, 2), (512, 1, 1)):
         s.sync_check()
         assert torch.isfinite(out["wavefields"][-1]).all()
         print(f"n={n} b={b} engine={eng}: ok, rmse {out['residual_rmse'][-1].tolist()}", flush=True)
+# batch sizes that take the balanced strips (chunks across image boundaries) and the packed narrow levels (several images per MMA, partly
+# filled last group), engine 2 only; HELMNET_PACK_NARROW=2 in the environment also packs the fused DoubleConv kernels
+s.set_engine(2)
+for n, b, iters in ((64, 41, 2), (96, 37, 2), (256, 37, 1), (128, 75, 1)):
+    s.set_domain_size(n, source_location=[n // 8, n // 2])
+    sos = (1.0 + 0.5 * torch.rand(b, 1, n, n, generator=g)).cuda()
+    out = s.forward(sos, num_iterations=iters)
+    s.sync_check()
+    assert torch.isfinite(out["wavefields"][-1]).all()
+    print(f"n={n} b={b} engine=2 (balanced / packed): ok", flush=True)
 print("done")
