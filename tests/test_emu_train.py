@@ -188,3 +188,38 @@ def test_two_sgd_steps_with_per_sample_sources_emulated(f_weights):
     for k in w_ref:                                                      # the UPDATE itself agrees to 1e-4
         d_ours, d_ref = w_ours[k].double() - f_weights[k].double(), w_ref[k] - f_weights[k].double()
         assert float((d_ours - d_ref).norm()) <= 1e-4 * float(d_ref.norm()) + 1e-7 * float(f_weights[k].double().norm()), k
+
+
+def golden_unroll(solver, g, device="cpu"):
+    """The training unroll of the reference-generated fixture tests/golden/train_unroll_n48.npz (oracle/make_golden_r2.py:
+    the UNMODIFIED reference's n_steps under autograd + backward) through this build.  Returns (loss, gparams, gwf, gres, gh)."""
+    n = int(g["wavefield"].shape[-1])
+    t = lambda k: torch.tensor(g[k]).to(device)
+    solver.set_domain_size(n, source_map=t("source"))
+    wf, res, h = (t(k).clone().requires_grad_(True) for k in ("wavefield", "residual", "hidden"))
+    for p in solver.f.parameters():
+        p.grad = None
+    solver.f.set_states(h, flatten=True)
+    out = solver.n_steps(wf, t("k_sq"), res, int(g["steps"]), True, True)
+    loss = 1e4 * torch.cat(out["residuals"]).pow(2).mean()
+    loss.backward()
+    gp = torch.cat([p.grad.reshape(-1) for p in solver.f.state_dict(keep_vars=True).values()])
+    return float(loss.detach()), gp, wf.grad, res.grad, h.grad
+
+
+def check_golden_unroll(ours, g, floor):
+    loss, gp, gwf, gres, gh = ours
+    assert abs(loss - float(g["loss_f64"])) / float(g["loss_f64"]) < max(1e-5, floor)
+    worst = {}
+    for name, a, k in (("parameters", gp, "gparams"), ("wavefield", gwf, "gwf"), ("residual", gres, "gres"), ("hidden", gh, "gh")):
+        e, e32 = rel_l2(a, g[k + "_f64"]), rel_l2(g[k + "_f32"], g[k + "_f64"])
+        worst[name] = (e, e32)
+        assert e < max(floor, 3 * e32), f"{name}: {e:.3e} (the reference's own fp32 run: {e32:.3e})"
+    return worst
+
+
+def test_unroll_gradients_reference_fixture_emulated(emu_trainable, gold):
+    """Gradients of the unmodified reference itself (fixture), fp64 run as the arbiter, bar 3 x the reference's fp32-vs-fp64 distance."""
+    g = gold("train_unroll_n48.npz")
+    worst = check_golden_unroll(golden_unroll(emu_trainable, g), g, floor=2e-5)
+    assert worst["parameters"][0] < 2e-5

@@ -602,6 +602,22 @@ def test_training_unroll_gradients(cuda_trainable, f_weights, n, batch, steps, e
     record("training_unroll_gradients", n=n, batch=batch, steps=steps, forward_engine=engine, worst=[f"{k}: {v[0]:.2e} (torch fp32 {v[1]:.2e})" for k, v in top])
 
 
+@pytest.mark.parametrize("engine,floor", [(0, 2e-5), (2, 3e-4)], ids=["fwd-simt", "fwd-tcgen05-fused"])
+def test_training_unroll_reference_fixture(cuda_trainable, gold, engine, floor):
+    """tests/golden/train_unroll_n48.npz: loss and gradients of the UNMODIFIED reference's own n_steps + backward() (48 x 48, batch 3,
+    per-sample sources, 3 unrolled steps from a mid-solve state; fp32 and fp64 runs).  This build against the fp64 run, within 3 x the
+    reference's own fp32-vs-fp64 distance (floor: see test_training_unroll_gradients)."""
+    from test_emu_train import check_golden_unroll, golden_unroll
+    s = cuda_trainable
+    s.set_engine(engine)
+    g = gold("train_unroll_n48.npz")
+    ours = golden_unroll(s, g, device="cuda:0")
+    s.sync_check()
+    s.set_engine(2)
+    worst = check_golden_unroll(ours, g, floor)
+    record("training_unroll_reference_fixture", forward_engine=engine, **{k: f"{v[0]:.2e} (reference fp32 {v[1]:.2e})" for k, v in worst.items()})
+
+
 def test_two_sgd_steps_with_per_sample_sources(f_weights):
     """training_step without the replay buffer, twice: per-sample source maps (hybridnet.py:398-399), hidden states handed in,
     n_steps under autograd, backward, an in-place SGD update -- the second unroll must run forward and backward on the updated
