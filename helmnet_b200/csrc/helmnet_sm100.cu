@@ -152,6 +152,7 @@ struct hn_ctx {
     int pack_narrow = 1;       // levels at most 62 pixels wide: several images per M = 128 MMA (HELMNET_PACK_NARROW: 0 off, 1 the down- /
                                // up-sampling kernels (default), 2 also the fused DoubleConv kernels -- measured: -0.5 .. -1.2 % per iteration
                                // at 256^2 x 32 / x 64 / 128^2 x 64, +1 % at 256^2 x 256, so it stays opt-in)
+    int bal_thresh = 100;      // balanced strips are taken when the model predicts at most this many per cent of the uniform cost (HELMNET_BAL_THRESH)
     int dconv_balance = 2;     // balanced strips where the model predicts a gain (HELMNET_DCONV_BALANCE: 0 off, 1 the fused DoubleConv
                                // kernels only, 2 also the down- / up-sampling kernels)
     bool fuse_bottom = true;   // decode[4] (the 8 -> 8 -> 8 DoubleConv at the bottom of the UNet) through the fused DoubleConv kernel
@@ -649,7 +650,7 @@ static int tcr_plan_strips(const hn_ctx* c, tcr::Args& t, int B) {
         const long long uniform_sm = per_sm ? ((long long)t.total_strips + c->num_sms - 1) / c->num_sms * (t.rows + 6) : 2 * rounds * (t.rows + 6);
         const long long vt = (long long)B * t.nsx * (t.H + tcr::BAL_PAD);
         const long long balanced = (vt + cap - 1) / cap + tcr::BAL_PAD + 2;
-        if (vt / cap >= 12 && 2 * balanced * 100 <= uniform_sm * 97) {
+        if (vt / cap >= 12 && 2 * balanced * 100 <= uniform_sm * c->bal_thresh) {
             t.bal = B * t.nsx;
             tgrid = cap;
             t.pdl_trig = c->pdl_mode == 1 || c->pdl_mode == 2;
@@ -875,7 +876,7 @@ static int launch_down(hn_ctx* c, int d, int B, cudaStream_t st) {
             const long long balanced = (vt + cap - 1) / cap + tcd::BAL_PAD + 2;
             // (uniform 32-row strips at 64+ rows per SM pair a long and a short strip list per SM: compare per SM, not per slot)
             const long long uniform_sm = (long long)B * (r / 2) / c->num_sms >= 64 ? ((long long)t.total_strips * (t.rows_o + 5) + c->num_sms - 1) / c->num_sms : 2 * uniform;
-            if (vt / cap >= 12 && 2 * balanced * 100 <= uniform_sm * 97) {
+            if (vt / cap >= 12 && 2 * balanced * 100 <= uniform_sm * c->bal_thresh) {
                 t.bal = B;
                 tgrid = cap;
                 t.pdl_trig = c->pdl_mode == 1 || c->pdl_mode == 2;
@@ -950,7 +951,7 @@ static int launch_up(hn_ctx* c, int d, int B, cudaStream_t st) {
             const long long uniform = (long long)((t.total_strips + tgrid - 1) / tgrid) * (t.rows_i + 6);
             const long long vt = (long long)B * (t.Hi + tcu::BAL_PAD);
             const long long balanced = (vt + cap - 1) / cap + tcu::BAL_PAD + 2;
-            if (vt / cap >= 12 && balanced * 100 <= uniform * 97) {
+            if (vt / cap >= 12 && balanced * 100 <= uniform * c->bal_thresh) {
                 t.bal = B;
                 tgrid = cap;
             }
@@ -1005,7 +1006,7 @@ static int launch_dconv_nh(hn_ctx* c, const tcf::Args& t0, int B, cudaStream_t s
         const long long uniform = (long long)((t.total_strips + grid - 1) / grid) * (t.rows + 7);
         const long long vt = (long long)B * (t.H + tcf::BAL_PAD);
         const long long balanced = (vt + cap - 1) / cap + tcf::BAL_PAD + 2;      // chunk + one strip start + even rounding
-        if (vt / cap >= 12 && balanced * 100 <= uniform * 97) {
+        if (vt / cap >= 12 && balanced * 100 <= uniform * c->bal_thresh) {
             t.bal = B;
             grid = cap;
             t.pdl_trig = c->pdl_mode == 1 || c->pdl_mode == 2;     // equal work per CTA: placement does not matter
@@ -1371,6 +1372,7 @@ int hn_create(hn_ctx** out, int device, int n, int max_batch, int pml_size, doub
     if (const char* pv = getenv("HELMNET_FUSE_BOTTOM")) c->fuse_bottom = atoi(pv) != 0;
     if (const char* pv = getenv("HELMNET_SIDE_STATE")) c->side_cfg = atoi(pv);
     if (const char* pv = getenv("HELMNET_DCONV_BALANCE")) c->dconv_balance = atoi(pv);
+    if (const char* pv = getenv("HELMNET_BAL_THRESH")) c->bal_thresh = atoi(pv);
     if (const char* pv = getenv("HELMNET_PACK_NARROW")) c->pack_narrow = atoi(pv);
     if (const char* pv = getenv("HELMNET_PACK_PENALTY")) c->pack_penalty = atoi(pv);
 #ifndef HN_EMU
