@@ -164,3 +164,41 @@ def test_evaluation_driver_outputs(tmp_path, gold):
     # same numbers as a direct forward
     ref = model.forward(sos, num_iterations=4, return_wavefields=True)
     assert rel_l2(torch.tensor(w[:, 3]), ref["wavefields"][3]) < 1e-6
+
+
+@pytest.mark.parametrize("batch,H,pad,grid", [(32, 256, 8, 148), (256, 256, 8, 148), (37, 128, 8, 296), (256, 128, 6, 296), (9, 512, 6, 296),
+                                              (100000, 256, 8, 148), (5, 64, 6, 296), (64, 8 * 512, 6, 296), (86, 32, 6, 296)])
+def test_balanced_strip_partition(batch, H, pad, grid):
+    """common.cuh: balanced_strip (the strip walk of the persistent tcgen05 kernels; executed here through a probe kernel on the
+    emulator).  Every row of every image belongs to exactly one strip, strips start and end on even rows, a CTA's strips are in
+    ascending order, and every CTA carries the same rows + pad * strips to within one strip start."""
+    import ctypes as C
+    from emu_backend import build_emu
+    dll = C.CDLL(build_emu())
+    cap = 3 + (batch * (H + pad) // grid) // (H + pad) + 3
+    out = (C.c_int * (grid * cap * 3))()
+    dll.emu_balanced_strips(batch, H, pad, grid, out, cap)
+    a = np.frombuffer(out, dtype=np.int32).reshape(grid, cap, 3)
+    covered = np.zeros((batch, H), np.int32) if batch * H < 5_000_000 else None
+    rows_total, costs, last = 0, [], (-1, -1)
+    for c in range(grid):
+        cost = 0
+        for i in range(cap):
+            b, y0, R = (int(v) for v in a[c, i])
+            if b < 0:
+                break
+            assert 0 <= b < batch and 0 <= y0 and R >= 2 and y0 + R <= H and y0 % 2 == 0 and R % 2 == 0
+            assert (b, y0) > last
+            last = (b, y0)
+            if covered is not None:
+                covered[b, y0:y0 + R] += 1
+            rows_total += R
+            cost += R + pad
+        else:
+            raise AssertionError("strip list not terminated")
+        costs.append(cost)
+    assert rows_total == batch * H
+    if covered is not None:
+        assert covered.min() == 1 and covered.max() == 1
+    busy = [x for x in costs if x > 0]
+    assert max(busy) - min(busy) <= 2 * pad + 4, (min(busy), max(busy))
